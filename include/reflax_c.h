@@ -1,0 +1,137 @@
+/* reflax_c.h — the drop-in boundary: a plain C ABI over the B200 (sm_100a) trace-and-shade path.
+ *
+ * ReflaxMan has no plugin/FFI layer; its hot path sits behind the public surface of the C++ classes Render, Scene
+ * and Camera (reference src/common/Render.h:22-41, Scene.h:29-39, Camera.h:50-52) whose only client is Pulse
+ * (reference Pulse.cpp:38,96,108-131,174-207,273-278,448-457).  Each entry point below names the reference member
+ * it stands in for.  The C++ shim in reflaxman_b200/shim/ (classes Render/Scene/Camera/... with the reference's
+ * names and members) forwards to these calls, so src/linux/main.cpp and src/windows/Main.cpp build against it
+ * unchanged; INTEGRATION.md shows the binding.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every input buffer (copied before return); the
+ * context owns all device memory; every call returns RFX_OK (0) or a negative error code and never throws
+ * (reference convention: no exceptions, bool/silent fallbacks — Render.cpp:143-144, Texture.cpp:34,175);
+ * rfx_last_error() gives the text.  One context drives one GPU from one host thread (the reference is
+ * single-threaded and non-reentrant).  There is no CPU fallback: without a usable sm_100 device
+ * rfx_create() fails.
+ *
+ * Framebuffer convention (reference Render.cpp:154-156, Color.cpp:114-117): row 0 is the BOTTOM scanline,
+ * ARGB is 0x00RRGGBB with alpha 0, channel = (unsigned char)(c * 255.999f).
+ */
+#ifndef REFLAX_C_H
+#define REFLAX_C_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFX_API __attribute__((visibility("default")))
+
+typedef struct rfx_ctx rfx_ctx;
+
+enum
+{
+  RFX_OK = 0,
+  RFX_ERR_ARG = -1,     /* bad argument / bad state (the reference would assert, then fall back silently) */
+  RFX_ERR_CUDA = -2,    /* CUDA runtime error (text in rfx_last_error) */
+  RFX_ERR_NODEV = -3,   /* no usable sm_100 device: there is no CPU fallback */
+  RFX_ERR_RNG = -4      /* random-stream ranking ran out of its over-provisioned draws (> 7 sigma event; fatal) */
+};
+
+enum { RFX_MT_METAL = 0, RFX_MT_DIELECTRIC = 1 };   /* reference Material.h:8 */
+
+typedef struct rfx_stats
+{
+  uint64_t rays;            /* bounce-loop iterations + shadow rays cast since rfx_stats_reset (SURVEY §8d "ray") */
+  uint64_t bounces;         /* reference Scene.cpp:80 iterations */
+  uint64_t shadow_rays;     /* reference Scene.cpp:125-143 */
+  uint64_t samples;         /* Scene::trace calls */
+  uint64_t kernel_launches; /* kernels of ours launched */
+  uint64_t h2d_bytes;       /* host->device bytes copied by the library */
+  uint64_t d2h_bytes;       /* device->host bytes copied by the library */
+  uint64_t trace_kernels;   /* K2 launches timed while profiling was enabled */
+  double trace_kernel_ms;   /* their summed device time (CUDA events on the launching stream); 0 unless rfx_enable_profiling */
+} rfx_stats;
+
+typedef struct rfx_device_info
+{
+  int device;
+  int sm_count;
+  int cc_major, cc_minor;
+  int clock_khz;            /* cudaDevAttrClockRate */
+  uint64_t total_mem;
+  char name[128];
+} rfx_device_info;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+/* Render::Render / ~Render (reference Render.cpp:5-23).  device = CUDA ordinal.  The context starts EMPTY (no
+ * default scene): the shim's Render::loadScene issues the reference's scene through the calls below. */
+RFX_API int rfx_create(rfx_ctx ** out, int device);
+RFX_API void rfx_destroy(rfx_ctx * ctx);
+RFX_API const char * rfx_last_error(const rfx_ctx * ctx);       /* ctx may be NULL: last rfx_create failure */
+RFX_API int rfx_get_device_info(const rfx_ctx * ctx, rfx_device_info * out);
+RFX_API const char * rfx_version(void);
+
+/* ---- scene (reference Scene.h:29-39; use at Render.cpp:32-54).  Objects keep insertion order: closest-hit
+ * ties go to the earlier object (reference Scene.cpp:98, strict <).  Upload happens lazily at rfx_render_begin,
+ * because the reference mutates triangles after insertion (Triangle::setTexture, Render.cpp:52-54). ---------- */
+RFX_API int rfx_scene_reset(rfx_ctx * ctx, const float ambient_rgb[3], float ambient_power);   /* Scene::Scene(Color,float), Scene.cpp:10-15 */
+RFX_API int rfx_add_light(rfx_ctx * ctx, const float origin[3], float radius, const float rgb[3], float power); /* Scene::addLight, Scene.cpp:47-58 -> light index */
+RFX_API int rfx_add_sphere(rfx_ctx * ctx, const float center[3], float radius, int mtype, const float rgb[3],
+                           float reflectivity, float transparency);                             /* Scene::addSphere, Scene.cpp:29-39 -> object index */
+RFX_API int rfx_add_triangle(rfx_ctx * ctx, const float v[9], int mtype, const float rgb[3], float reflectivity,
+                             float transparency);                                               /* Scene::addTriangle, Scene.cpp:41-46 -> object index */
+RFX_API int rfx_set_triangle_texture(rfx_ctx * ctx, int object, int texture, const float uv[6]); /* Triangle::setTexture, Triangle.cpp:110-120 (u1,v1,u2,v2,u3,v3) */
+RFX_API int rfx_add_plane(rfx_ctx * ctx, const float pos[3], const float norm[3], int mtype, const float rgb[3],
+                          float reflectivity, float transparency);                              /* Plane::Plane, Plane.cpp:9-14 (no Scene::addPlane exists upstream) */
+/* Scene::addTexture (Scene.cpp:60-65) with the pixels already decoded (0xAARRGGBB, row 0 = v 0, Texture.cpp:34-108).
+ * argb == NULL or w*h == 0 is a texture whose file failed to load: sampling it gives the reference's grey
+ * checker (Texture.cpp:242-243).  Returns the texture id. */
+RFX_API int rfx_add_texture_argb(rfx_ctx * ctx, uint32_t w, uint32_t h, const uint32_t * argb);
+RFX_API int rfx_set_skybox(rfx_ctx * ctx, int texture);   /* Scene::setSkyboxTexture / Skybox::loadTexture, Skybox.cpp:21-37; -1 or an empty texture = none */
+
+/* ---- camera (reference Camera.h:50-52; snapshot taken by renderBegin, Render.cpp:125-126) ------------------ */
+RFX_API int rfx_set_camera(rfx_ctx * ctx, const float eye[3], const float view[9] /* row-major _11.._33 */, float fov);
+
+/* ---- random streams (reference trace_math.h:34-39).  seed_vector3 drives Vector3::randomInsideSphere
+ * (one randDir per Scene::trace call, Scene.cpp:75); seed_render drives the additive-mode pixel jitter
+ * (Render.cpp:177-178).  Both streams continue across frames exactly as in one reference process. ----------- */
+RFX_API int rfx_set_seeds(rfx_ctx * ctx, uint32_t seed_vector3, uint32_t seed_render);
+RFX_API int rfx_get_seeds(rfx_ctx * ctx, uint32_t out[2]);            /* current LCG states (synchronises) */
+RFX_API int rfx_skip_samples(rfx_ctx * ctx, uint64_t n_trace_calls);  /* advance the randDir stream as if n Scene::trace calls had run (frame sharding) */
+
+/* ---- Render (reference Render.h:30-41) ----------------------------------------------------------------- */
+RFX_API int rfx_set_image_size(rfx_ctx * ctx, uint32_t width, uint32_t height);   /* Render::setImageSize, Render.cpp:57-80 */
+RFX_API int rfx_render_begin(rfx_ctx * ctx, int reflect_num, int sample_num, int additive); /* Render::renderBegin, Render.cpp:116-134 */
+RFX_API int rfx_render_next(rfx_ctx * ctx, uint32_t pixels);   /* Render::renderNext, Render.cpp:136-215: 1 = more to do, 0 = frame complete, <0 error */
+RFX_API float rfx_progress(const rfx_ctx * ctx);               /* Render::getRenderProgress, Render.cpp:223-226 (percent) */
+RFX_API int rfx_additive_counter(const rfx_ctx * ctx);         /* Render::additiveCounter */
+RFX_API int rfx_in_progress(const rfx_ctx * ctx);              /* Render::inProgress */
+RFX_API int rfx_read_argb(rfx_ctx * ctx, uint32_t * dst);      /* imagePixel(x,y).argb() for the whole image (Pulse.cpp:455-458 / Render::copyImage, Render.cpp:82-101) */
+RFX_API int rfx_read_rgbf(rfx_ctx * ctx, float * dst);         /* imagePixel(x,y) for the whole image, 3 floats per pixel (Render.cpp:103-114) */
+RFX_API int rfx_read_pixel(rfx_ctx * ctx, int x, int y, float rgb[3]);            /* Render::imagePixel(x,y) */
+RFX_API int rfx_read_signatures(rfx_ctx * ctx, uint32_t * dst); /* per-pixel hit-path signature of the last pass (parity localiser; enabled by rfx_enable_signatures) */
+RFX_API int rfx_enable_signatures(rfx_ctx * ctx, int on);
+
+/* ---- headless batch path (the bench driver; models Pulse's screenshot flow, Pulse.cpp:174-208, for a camera
+ * path).  cams = n_frames x 13 floats (eye[3], view[9], fov).  Each frame is setImageSize-sized, rendered with
+ * renderBegin(reflect_num, sample_num, false) + renderNext to completion, and packed with imagePixel().argb().
+ * The randDir stream continues from frame to frame. ------------------------------------------------------- */
+/* output to HOST memory (n_frames * W * H uint32); device->host copies are overlapped with the next frame */
+RFX_API int rfx_render_frames(rfx_ctx * ctx, int n_frames, const float * cams, int reflect_num, int sample_num, uint32_t * argb_host);
+/* output to DEVICE memory the caller owns, on the caller's stream (cudaStream_t as void*; NULL = context stream);
+ * asynchronous: returns after enqueueing */
+RFX_API int rfx_render_frames_device(rfx_ctx * ctx, int n_frames, const float * cams, int reflect_num, int sample_num,
+                                     uint32_t * argb_device, void * stream);
+RFX_API int rfx_synchronize(rfx_ctx * ctx);
+
+/* ---- bookkeeping --------------------------------------------------------------------------------------- */
+RFX_API int rfx_get_stats(rfx_ctx * ctx, rfx_stats * out);     /* synchronises */
+RFX_API int rfx_stats_reset(rfx_ctx * ctx);
+RFX_API int rfx_enable_profiling(rfx_ctx * ctx, int on);       /* bracket every K2 launch with CUDA events (bench roofline) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REFLAX_C_H */

@@ -1,0 +1,45 @@
+"""Builds the CUDA extension in-tree: reflaxman_b200/libreflax_b200.so (sm_100a only, no other arch, no fallback).
+
+nvcc cross-compiles without a GPU.  The flags matter for parity: --fmad=false (no FMA contraction in device code),
+-ffp-contract=off for the host-side scene flattening, and no fast-math anywhere (IEEE div/sqrt, denormals kept).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = [os.path.join(HERE, "csrc", f) for f in ("rfx_kernels.cu", "rfx_capi.cu")]
+HDR = [os.path.join(HERE, "csrc", f) for f in ("rfx_kernels.h", "rfx_types.h")] + [os.path.join(HERE, "..", "include", "reflax_c.h")]
+OUT = os.path.join(HERE, "libreflax_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "--fmad=false", "-std=c++17",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-O2",
+    "-shared",
+]
+
+
+def stale():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(p) > t for p in SRC + HDR + [os.path.abspath(__file__)])
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", OUT, *SRC]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)

@@ -1,0 +1,273 @@
+"""ctypes binding of the C ABI (include/reflax_c.h) — what the tests and bench.py call.
+
+This is deliberately thin: every method is one C call.  The library is the in-tree
+``reflaxman_b200/libreflax_b200.so`` (sm_100a only).  There is no CPU fallback: if the library is missing or no B200
+is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libreflax_b200.so")
+
+_fp = C.POINTER(C.c_float)
+_u32p = C.POINTER(C.c_uint32)
+
+
+class RfxStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays", "bounces", "shadow_rays", "samples", "kernel_launches",
+                                          "h2d_bytes", "d2h_bytes", "trace_kernels")] + [("trace_kernel_ms", C.c_double)]
+
+    def as_dict(self):
+        return {n: (float if n == "trace_kernel_ms" else int)(getattr(self, n)) for n, _ in self._fields_}
+
+
+class RfxDeviceInfo(C.Structure):
+    _fields_ = [("device", C.c_int), ("sm_count", C.c_int), ("cc_major", C.c_int), ("cc_minor", C.c_int),
+                ("clock_khz", C.c_int), ("total_mem", C.c_uint64), ("name", C.c_char * 128)]
+
+
+# every symbol include/reflax_c.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("rfx_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    ("rfx_destroy", None, [C.c_void_p]),
+    ("rfx_last_error", C.c_char_p, [C.c_void_p]),
+    ("rfx_get_device_info", C.c_int, [C.c_void_p, C.POINTER(RfxDeviceInfo)]),
+    ("rfx_version", C.c_char_p, []),
+    ("rfx_scene_reset", C.c_int, [C.c_void_p, _fp, C.c_float]),
+    ("rfx_add_light", C.c_int, [C.c_void_p, _fp, C.c_float, _fp, C.c_float]),
+    ("rfx_add_sphere", C.c_int, [C.c_void_p, _fp, C.c_float, C.c_int, _fp, C.c_float, C.c_float]),
+    ("rfx_add_triangle", C.c_int, [C.c_void_p, _fp, C.c_int, _fp, C.c_float, C.c_float]),
+    ("rfx_set_triangle_texture", C.c_int, [C.c_void_p, C.c_int, C.c_int, _fp]),
+    ("rfx_add_plane", C.c_int, [C.c_void_p, _fp, _fp, C.c_int, _fp, C.c_float, C.c_float]),
+    ("rfx_add_texture_argb", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _u32p]),
+    ("rfx_set_skybox", C.c_int, [C.c_void_p, C.c_int]),
+    ("rfx_set_camera", C.c_int, [C.c_void_p, _fp, _fp, C.c_float]),
+    ("rfx_set_seeds", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    ("rfx_get_seeds", C.c_int, [C.c_void_p, _u32p]),
+    ("rfx_skip_samples", C.c_int, [C.c_void_p, C.c_uint64]),
+    ("rfx_set_image_size", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    ("rfx_render_begin", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    ("rfx_render_next", C.c_int, [C.c_void_p, C.c_uint32]),
+    ("rfx_progress", C.c_float, [C.c_void_p]),
+    ("rfx_additive_counter", C.c_int, [C.c_void_p]),
+    ("rfx_in_progress", C.c_int, [C.c_void_p]),
+    ("rfx_read_argb", C.c_int, [C.c_void_p, _u32p]),
+    ("rfx_read_rgbf", C.c_int, [C.c_void_p, _fp]),
+    ("rfx_read_pixel", C.c_int, [C.c_void_p, C.c_int, C.c_int, _fp]),
+    ("rfx_read_signatures", C.c_int, [C.c_void_p, _u32p]),
+    ("rfx_enable_signatures", C.c_int, [C.c_void_p, C.c_int]),
+    ("rfx_render_frames", C.c_int, [C.c_void_p, C.c_int, _fp, C.c_int, C.c_int, C.c_void_p]),
+    ("rfx_render_frames_device", C.c_int, [C.c_void_p, C.c_int, _fp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    ("rfx_synchronize", C.c_int, [C.c_void_p]),
+    ("rfx_get_stats", C.c_int, [C.c_void_p, C.POINTER(RfxStats)]),
+    ("rfx_stats_reset", C.c_int, [C.c_void_p]),
+    ("rfx_enable_profiling", C.c_int, [C.c_void_p, C.c_int]),
+]
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree extension; fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("reflaxman_b200: %s is missing — run `python -m reflaxman_b200.build` "
+                               "(or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)   # AttributeError if the library does not export what the header declares
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class RfxError(RuntimeError):
+    pass
+
+
+def _f(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(_fp)
+
+
+def pack_cameras(cams):
+    """[(eye[3], view[9], fov), ...] -> contiguous float32 [n, 13] as rfx_render_frames expects."""
+    out = np.zeros((len(cams), 13), np.float32)
+    for i, (eye, view, fov) in enumerate(cams):
+        out[i, 0:3] = eye
+        out[i, 3:12] = view
+        out[i, 12] = fov
+    return out
+
+
+class Context:
+    """One rfx_ctx: one GPU, one host thread (the reference's Render is single-threaded and non-reentrant)."""
+
+    def __init__(self, device=0):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.rfx_create(C.byref(h), device)
+        if rc != 0:
+            raise RfxError("rfx_create failed (%d): %s" % (rc, self.L.rfx_last_error(None).decode()))
+        self.h = h
+        self.W = self.H = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rfx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc < 0:
+            raise RfxError("%s failed (%d): %s" % (what, rc, self.L.rfx_last_error(self.h).decode()))
+        return rc
+
+    # ---- scene -----------------------------------------------------------------------------------------------
+    def load_scene(self, scene):
+        """Issue a scenes.py dict through the scene-building calls, in the reference's order (Render.cpp:32-54)."""
+        rgb, p = scene["ambient"]
+        self._ck(self.L.rfx_scene_reset(self.h, _f(rgb)[1], C.c_float(p)), "rfx_scene_reset")
+        tex_ids = []
+        for t in scene["textures"]:
+            tex_ids.append(self.add_texture(t))
+        if scene.get("skybox") is not None:
+            self._ck(self.L.rfx_set_skybox(self.h, self.add_texture(scene["skybox"])), "rfx_set_skybox")
+        for o, r, c, pw in scene["lights"]:
+            self._ck(self.L.rfx_add_light(self.h, _f(o)[1], C.c_float(r), _f(c)[1], C.c_float(pw)), "rfx_add_light")
+        for ob in scene["objects"]:
+            if ob[0] == "sphere":
+                _, c, r, mt, col, refl, tr = ob
+                self._ck(self.L.rfx_add_sphere(self.h, _f(c)[1], C.c_float(r), mt, _f(col)[1], C.c_float(refl), C.c_float(tr)), "rfx_add_sphere")
+            elif ob[0] == "tri":
+                _, v, mt, col, refl, tr, tex, uv = ob
+                idx = self._ck(self.L.rfx_add_triangle(self.h, _f(v)[1], mt, _f(col)[1], C.c_float(refl), C.c_float(tr)), "rfx_add_triangle")
+                if tex >= 0:
+                    self._ck(self.L.rfx_set_triangle_texture(self.h, idx, tex_ids[tex], _f(uv)[1]), "rfx_set_triangle_texture")
+            elif ob[0] == "plane":
+                _, pos, nrm, mt, col, refl, tr = ob
+                self._ck(self.L.rfx_add_plane(self.h, _f(pos)[1], _f(nrm)[1], mt, _f(col)[1], C.c_float(refl), C.c_float(tr)), "rfx_add_plane")
+            else:
+                raise ValueError(ob[0])
+
+    def add_texture(self, argb):
+        if argb is None:
+            return self._ck(self.L.rfx_add_texture_argb(self.h, 0, 0, None), "rfx_add_texture_argb")
+        a = np.ascontiguousarray(argb, dtype=np.uint32)
+        return self._ck(self.L.rfx_add_texture_argb(self.h, a.shape[1], a.shape[0], a.ctypes.data_as(_u32p)), "rfx_add_texture_argb")
+
+    # ---- camera / seeds ----------------------------------------------------------------------------------------
+    def set_camera(self, cam):
+        eye, view, fov = cam
+        self._ck(self.L.rfx_set_camera(self.h, _f(eye)[1], _f(view)[1], C.c_float(fov)), "rfx_set_camera")
+
+    def set_seeds(self, seed_vector3=12345, seed_render=12345):
+        self._ck(self.L.rfx_set_seeds(self.h, seed_vector3 & 0xFFFFFFFF, seed_render & 0xFFFFFFFF), "rfx_set_seeds")
+
+    def get_seeds(self):
+        out = (C.c_uint32 * 2)()
+        self._ck(self.L.rfx_get_seeds(self.h, out), "rfx_get_seeds")
+        return int(out[0]), int(out[1])
+
+    def skip_samples(self, n):
+        self._ck(self.L.rfx_skip_samples(self.h, n), "rfx_skip_samples")
+
+    # ---- Render ------------------------------------------------------------------------------------------------
+    def set_image_size(self, w, h):
+        self._ck(self.L.rfx_set_image_size(self.h, w, h), "rfx_set_image_size")
+        self.W, self.H = int(w), int(h)
+
+    def render_begin(self, refl, samples=1, additive=False):
+        self._ck(self.L.rfx_render_begin(self.h, refl, samples, 1 if additive else 0), "rfx_render_begin")
+
+    def render_next(self, pixels):
+        return self._ck(self.L.rfx_render_next(self.h, pixels), "rfx_render_next") == 1
+
+    def render(self, cam, refl, samples=1, additive=False, chunk=None):
+        """renderBegin + renderNext(chunk) until done, as Pulse does (reference Pulse.cpp:124-131,176-186)."""
+        self.set_camera(cam)
+        self.render_begin(refl, samples, additive)
+        chunk = chunk or self.W * self.H
+        while self.render_next(chunk):
+            pass
+        return self
+
+    def progress(self):
+        return float(self.L.rfx_progress(self.h))
+
+    def additive_counter(self):
+        return int(self.L.rfx_additive_counter(self.h))
+
+    def in_progress(self):
+        return bool(self.L.rfx_in_progress(self.h))
+
+    def read_argb(self):
+        out = np.empty((self.H, self.W), np.uint32)
+        self._ck(self.L.rfx_read_argb(self.h, out.ctypes.data_as(_u32p)), "rfx_read_argb")
+        return out
+
+    def read_rgbf(self):
+        out = np.empty((self.H, self.W, 3), np.float32)
+        self._ck(self.L.rfx_read_rgbf(self.h, out.ctypes.data_as(_fp)), "rfx_read_rgbf")
+        return out
+
+    def read_pixel(self, x, y):
+        out = (C.c_float * 3)()
+        self._ck(self.L.rfx_read_pixel(self.h, x, y, out), "rfx_read_pixel")
+        return np.array(out[:], np.float32)
+
+    def enable_signatures(self, on=True):
+        self._ck(self.L.rfx_enable_signatures(self.h, 1 if on else 0), "rfx_enable_signatures")
+
+    def read_signatures(self):
+        out = np.empty((self.H, self.W), np.uint32)
+        self._ck(self.L.rfx_read_signatures(self.h, out.ctypes.data_as(_u32p)), "rfx_read_signatures")
+        return out
+
+    # ---- batch -------------------------------------------------------------------------------------------------
+    def render_frames(self, cams, refl, samples=1, out=None):
+        """Host-buffer batch render; ``out``: uint32 array [n, H, W] (pinned for full copy/compute overlap)."""
+        packed = cams if isinstance(cams, np.ndarray) else pack_cameras(cams)
+        n = packed.shape[0]
+        if out is None:
+            out = np.empty((n, self.H, self.W), np.uint32)
+        ptr = out.ctypes.data if isinstance(out, np.ndarray) else int(out)
+        self._ck(self.L.rfx_render_frames(self.h, n, packed.ctypes.data_as(_fp), refl, samples, C.c_void_p(ptr)), "rfx_render_frames")
+        return out
+
+    def render_frames_device(self, cams, refl, samples, argb_device_ptr, stream=0):
+        packed = cams if isinstance(cams, np.ndarray) else pack_cameras(cams)
+        self._ck(self.L.rfx_render_frames_device(self.h, packed.shape[0], packed.ctypes.data_as(_fp), refl, samples,
+                                                 C.c_void_p(int(argb_device_ptr)), C.c_void_p(int(stream))), "rfx_render_frames_device")
+
+    def synchronize(self):
+        self._ck(self.L.rfx_synchronize(self.h), "rfx_synchronize")
+
+    def stats(self):
+        s = RfxStats()
+        self._ck(self.L.rfx_get_stats(self.h, C.byref(s)), "rfx_get_stats")
+        return s.as_dict()
+
+    def stats_reset(self):
+        self._ck(self.L.rfx_stats_reset(self.h), "rfx_stats_reset")
+
+    def enable_profiling(self, on=True):
+        self._ck(self.L.rfx_enable_profiling(self.h, 1 if on else 0), "rfx_enable_profiling")
+
+    def device_info(self):
+        d = RfxDeviceInfo()
+        self._ck(self.L.rfx_get_device_info(self.h, C.byref(d)), "rfx_get_device_info")
+        return {"device": d.device, "sm_count": d.sm_count, "cc": (d.cc_major, d.cc_minor), "clock_khz": d.clock_khz,
+                "total_mem": int(d.total_mem), "name": d.name.decode()}

@@ -1,0 +1,911 @@
+// rfx_capi.cu — the C ABI of include/reflax_c.h: context, host-side scene flattening, slice scheduling.
+//
+// Host-side float arithmetic in this file (triangle basis inversion, envColor, skybox half-tile, sqRadius, rz)
+// restates what the reference's constructors compute once per object/frame; it is compiled with
+// -ffp-contract=off so every operation is the same IEEE binary32 operation the reference's build performs
+// (reference Triangle.cpp:11-21,110-120; Matrix33.cpp:10-15,49-79; Scene.cpp:10-15,47-58; Skybox.cpp:21-37;
+// Sphere.cpp:9-20; Material.cpp:8-14; OmniLight.cpp:8-14; Render.cpp:148-150).
+#include "../../include/reflax_c.h"
+#include "rfx_kernels.h"
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace rfx;
+
+namespace
+{
+
+const float VSN = 1.08420217248550443e-19f;   // sqrtf(FLT_MIN), reference trace_math.h:17
+std::string g_createError;
+
+struct HostTex { uint32_t w = 0, h = 0; std::vector<uint32_t> px; uint32_t * dev = nullptr; bool uploaded = false; };
+struct HostObj
+{
+  int kind;                 // 0 sphere, 1 triangle, 2 plane
+  Material mat;             // order = insertion index
+  float center[3], sqRadius;
+  Triangle tri;
+  Plane plane;
+};
+
+inline float clampf(float v, float lo, float hi) { return v < lo ? lo : v > hi ? hi : v; }
+
+struct H3 { float x, y, z; };
+inline H3 hsub(H3 a, H3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+inline H3 hcross(H3 a, H3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }   // Vector3.cpp:136-141
+inline H3 hnormalize(H3 a)   // trace_math.cpp:3-12
+{
+  const float l = sqrtf((a.x * a.x + a.y * a.y) + a.z * a.z);
+  if (l > VSN) return { a.x / l, a.y / l, a.z / l };
+  return a;
+}
+
+// Matrix33(u, v, n) columns + invert(), reference Matrix33.cpp:10-15, 49-79
+void invertColumns(H3 u, H3 v, H3 n, float out[9])
+{
+  const float _11 = u.x, _12 = v.x, _13 = n.x, _21 = u.y, _22 = v.y, _23 = n.y, _31 = u.z, _32 = v.z, _33 = n.z;
+  const float d = (_11 * (_22 * _33 - _32 * _23) + _21 * (_32 * _13 - _12 * _33)) + _31 * (_12 * _23 - _13 * _22);
+  if (fabsf(d) > VSN)
+  {
+    out[0] = (_22 * _33 - _23 * _32) / d; out[1] = (_13 * _32 - _12 * _33) / d; out[2] = (_12 * _23 - _13 * _22) / d;
+    out[3] = (_23 * _31 - _21 * _33) / d; out[4] = (_11 * _33 - _13 * _31) / d; out[5] = (_13 * _21 - _11 * _23) / d;
+    out[6] = (_21 * _32 - _22 * _31) / d; out[7] = (_12 * _31 - _11 * _32) / d; out[8] = (_11 * _22 - _12 * _21) / d;
+  }
+  else
+  {
+    const float id[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    memcpy(out, id, sizeof(id));
+  }
+}
+
+template <typename T> inline size_t align16(T v) { return ((size_t)v + 15) & ~(size_t)15; }
+
+} // namespace
+
+struct rfx_ctx
+{
+  int device = 0;
+  cudaStream_t stream = nullptr, copyStream = nullptr, lastStream = nullptr;
+  cudaDeviceProp prop;
+  mutable std::string err;
+
+  // ---- host scene
+  float ambient[3] = { 0, 0, 0 }, ambientPower = 0, env[3] = { 0, 0, 0 };
+  std::vector<Light> lights;
+  std::vector<HostObj> objs;
+  std::vector<HostTex> tex;
+  int skyTex = -1;
+  bool sceneDirty = true;
+
+  // ---- device scene
+  unsigned char * dBlob = nullptr; size_t blobCap = 0; uint32_t blobBytes = 0;
+  float * dLut = nullptr;
+
+  // ---- camera + render state (reference Render.h:9-27)
+  float eye[3] = { 0, 0, 0 }, view[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, fov = 1.0f;
+  uint32_t W = 0, H = 0;
+  float * dImage = nullptr; size_t imageCap = 0;
+  uint32_t * dSig = nullptr; size_t sigCap = 0; bool sigOn = false;
+  int reflNum = 0, sampleNum = 0; bool additive = false; int additiveCounter = 0; bool inProgress = false;
+  uint64_t cursor = 0;
+  FrameParams snap;           // camera snapshot taken by render_begin
+
+  // ---- random streams
+  uint32_t * dRng = nullptr;  // [2] ping-pong LCG state of the Vector3.cpp TU stream
+  int rngSlot = 0;
+  uint32_t seedRender = 12345u;
+  uint32_t * dBlockCounts = nullptr, * dBlockOffsets = nullptr; size_t blocksCap = 0, offsCap = 0;
+  uint32_t * dSampleStates = nullptr; size_t statesCap = 0;
+  int * dStatus = nullptr;
+
+  // ---- staging for the host batch path
+  uint32_t * dFrame[3] = { nullptr, nullptr, nullptr }; size_t frameCap = 0;
+  cudaEvent_t evRendered[3] = { nullptr, nullptr, nullptr }, evCopied[3] = { nullptr, nullptr, nullptr };
+
+  // ---- counters
+  unsigned long long * dCounters = nullptr;   // [32][2]
+  rfx_stats stats;
+  bool profiling = false;
+  std::vector<cudaEvent_t> evPool;            // pairs (start, stop) around K2 launches while profiling
+  size_t evUsed = 0;
+};
+
+namespace
+{
+
+int fail(const rfx_ctx * c, int code, const std::string & msg)
+{
+  if (c) c->err = msg; else g_createError = msg;
+  return code;
+}
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(ctx, RFX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+
+int useStream(rfx_ctx * ctx, cudaStream_t st)
+{
+  if (ctx->lastStream && ctx->lastStream != st) CK(cudaStreamSynchronize(ctx->lastStream));
+  ctx->lastStream = st;
+  return RFX_OK;
+}
+
+template <typename T> int ensure(rfx_ctx * ctx, T *& p, size_t & cap, size_t need)
+{
+  if (need <= cap) return RFX_OK;
+  if (p) { CK(cudaDeviceSynchronize()); CK(cudaFree(p)); p = nullptr; cap = 0; }
+  const size_t want = need + need / 8;
+  CK(cudaMalloc((void **)&p, want * sizeof(T)));
+  cap = want;
+  return RFX_OK;
+}
+
+Material makeMaterial(int mtype, const float rgb[3], float refl, float transp, int order)   // Material.cpp:8-14
+{
+  Material m;
+  m.r = rgb[0]; m.g = rgb[1]; m.b = rgb[2];
+  m.reflectivity = clampf(refl, 0.0f, 1.0f);
+  (void)transp;   // clamped and stored by the reference, never read by the tracer
+  m.type = mtype ? 1 : 0;
+  m.order = order;
+  m.tex = -1;
+  m.pad = 0;
+  return m;
+}
+
+// flatten the host scene into the blob layout described in rfx_types.h and upload it
+int uploadScene(rfx_ctx * ctx, cudaStream_t st)
+{
+  if (!ctx->sceneDirty) return RFX_OK;
+
+  for (HostTex & t : ctx->tex)
+    if (!t.uploaded)
+    {
+      if (!t.px.empty())
+      {
+        CK(cudaMalloc((void **)&t.dev, t.px.size() * 4));
+        CK(cudaMemcpyAsync(t.dev, t.px.data(), t.px.size() * 4, cudaMemcpyHostToDevice, st));
+        ctx->stats.h2d_bytes += t.px.size() * 4;
+      }
+      t.uploaded = true;
+    }
+
+  std::vector<const HostObj *> sph, tri, pla;
+  for (const HostObj & o : ctx->objs) (o.kind == 0 ? sph : o.kind == 1 ? tri : pla).push_back(&o);
+
+  SceneHeader h;
+  memset(&h, 0, sizeof(h));
+  h.nSpheres = (int)sph.size(); h.nTris = (int)tri.size(); h.nPlanes = (int)pla.size();
+  h.nLights = (int)ctx->lights.size(); h.nTextures = (int)ctx->tex.size();
+  h.skyTex = ctx->skyTex;
+  memcpy(h.ambient, ctx->ambient, sizeof(h.ambient));
+  h.ambientPower = ctx->ambientPower;
+  memcpy(h.env, ctx->env, sizeof(h.env));
+  // Skybox::loadTexture / Skybox::Skybox, Skybox.cpp:6-7,21-37
+  if (ctx->skyTex >= 0)
+  {
+    h.halfTileW = (1.0f / 8.0f - 1.0f / float(ctx->tex[ctx->skyTex].w)) - FLT_EPSILON;
+    h.halfTileH = (1.0f / 6.0f - 1.0f / float(ctx->tex[ctx->skyTex].h)) - FLT_EPSILON;
+  }
+  else
+  {
+    h.halfTileW = 1.0f / 8.0f - FLT_EPSILON;
+    h.halfTileH = 1.0f / 6.0f - FLT_EPSILON;
+  }
+  size_t off = align16(sizeof(SceneHeader));
+  h.offLights = (uint32_t)off; off = align16(off + sizeof(Light) * ctx->lights.size());
+  h.offSpheres = (uint32_t)off; off = align16(off + sizeof(float) * 4 * sph.size());
+  h.offTris = (uint32_t)off; off = align16(off + sizeof(Triangle) * tri.size());
+  h.offPlanes = (uint32_t)off; off = align16(off + sizeof(Plane) * pla.size());
+  h.offMats = (uint32_t)off; off = align16(off + sizeof(Material) * ctx->objs.size());
+  h.offTex = (uint32_t)off; off = align16(off + sizeof(TexRef) * ctx->tex.size());
+  h.bytes = (uint32_t)off;
+  h.byteLut = ctx->dLut;
+  if (off > 200 * 1024) return fail(ctx, RFX_ERR_ARG, "scene too large for the shared-memory resident layout (200 KB)");
+
+  std::vector<unsigned char> blob(off, 0);
+  memcpy(blob.data(), &h, sizeof(h));
+  if (!ctx->lights.empty()) memcpy(blob.data() + h.offLights, ctx->lights.data(), sizeof(Light) * ctx->lights.size());
+  Material * mats = reinterpret_cast<Material *>(blob.data() + h.offMats);
+  size_t mi = 0;
+  for (size_t i = 0; i < sph.size(); i++)
+  {
+    float * d = reinterpret_cast<float *>(blob.data() + h.offSpheres) + 4 * i;
+    d[0] = sph[i]->center[0]; d[1] = sph[i]->center[1]; d[2] = sph[i]->center[2]; d[3] = sph[i]->sqRadius;
+    mats[mi++] = sph[i]->mat;
+  }
+  for (size_t i = 0; i < tri.size(); i++)
+  {
+    reinterpret_cast<Triangle *>(blob.data() + h.offTris)[i] = tri[i]->tri;
+    mats[mi++] = tri[i]->mat;
+  }
+  for (size_t i = 0; i < pla.size(); i++)
+  {
+    reinterpret_cast<Plane *>(blob.data() + h.offPlanes)[i] = pla[i]->plane;
+    mats[mi++] = pla[i]->mat;
+  }
+  for (size_t i = 0; i < ctx->tex.size(); i++)
+  {
+    TexRef r;
+    r.px = ctx->tex[i].dev; r.w = ctx->tex[i].w; r.h = ctx->tex[i].h;
+    reinterpret_cast<TexRef *>(blob.data() + h.offTex)[i] = r;
+  }
+
+  if (off > ctx->blobCap)
+  {
+    if (ctx->dBlob) { CK(cudaDeviceSynchronize()); CK(cudaFree(ctx->dBlob)); ctx->dBlob = nullptr; }
+    CK(cudaMalloc((void **)&ctx->dBlob, off));
+    ctx->blobCap = off;
+  }
+  // pageable source: the copy is staged before the call returns, so the local vector may die
+  CK(cudaMemcpyAsync(ctx->dBlob, blob.data(), off, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  ctx->stats.h2d_bytes += off;
+  ctx->blobBytes = (uint32_t)off;
+  ctx->sceneDirty = false;
+  return RFX_OK;
+}
+
+// number of block-preview origins (x % a == 0 && y % a == 0) with linear index < p, scan order
+uint64_t originsBefore(uint64_t p, uint32_t W, uint32_t a)
+{
+  const uint64_t bw = (W + a - 1) / a;
+  const uint64_t y = p / W, x = p % W;
+  uint64_t n = ((y + a - 1) / a) * bw;            // complete origin rows below y
+  if (y % a == 0) n += (x + a - 1) / a;           // origins left of x in this row
+  return n;
+}
+
+// rank n Scene::trace calls on the randDir stream; the states land in ctx->dSampleStates (or nowhere when skipOnly)
+int rankSamples(rfx_ctx * ctx, uint64_t n, bool skipOnly, cudaStream_t st)
+{
+  if (n == 0) return RFX_OK;
+  const uint32_t nBlocks = rngBlocksFor(n);
+  int rc;
+  if ((rc = ensure(ctx, ctx->dBlockCounts, ctx->blocksCap, nBlocks)) != RFX_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dBlockOffsets, ctx->offsCap, nBlocks)) != RFX_OK) return rc;
+  if (!skipOnly && (rc = ensure(ctx, ctx->dSampleStates, ctx->statesCap, n)) != RFX_OK) return rc;
+  RngWork w;
+  w.stateIn = ctx->dRng + ctx->rngSlot;
+  w.stateOut = ctx->dRng + (ctx->rngSlot ^ 1);
+  w.blockCounts = ctx->dBlockCounts;
+  w.blockOffsets = ctx->dBlockOffsets;
+  w.sampleStates = skipOnly ? nullptr : ctx->dSampleStates;
+  w.status = ctx->dStatus;
+  w.n = n;
+  w.nBlocks = nBlocks;
+  ctx->stats.kernel_launches += launchRngRank(w, st);
+  CK(cudaGetLastError());
+  ctx->rngSlot ^= 1;
+  return RFX_OK;
+}
+
+const uint64_t MAX_CALLS_PER_LAUNCH = 1ull << 25;   // bounds the ranked-state scratch (128 MB) for huge SSAA factors / 8K frames
+
+// render pixels [p0, p1) of the frame latched by render_begin
+int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, bool writeImage, cudaStream_t st)
+{
+  int rc;
+  const int sn = ctx->sampleNum;
+  uint64_t cur = p0;
+  while (cur < p1)
+  {
+    uint64_t end, nCalls, firstRank = 0;
+    if (sn > 0)
+    {
+      const uint64_t per = (uint64_t)sn * sn;
+      uint64_t pix = MAX_CALLS_PER_LAUNCH / per;
+      if (pix < 1) pix = 1;
+      end = std::min(p1, cur + pix);
+      nCalls = (end - cur) * per;
+    }
+    else
+    {
+      const uint32_t a = (uint32_t)(-sn);
+      end = p1;   // at most one call per a*a pixels: never exceeds the cap for any sane image
+      firstRank = originsBefore(cur, ctx->W, a);
+      nCalls = originsBefore(end, ctx->W, a) - firstRank;
+    }
+    if (nCalls > 0)
+    {
+      if ((rc = rankSamples(ctx, nCalls, false, st)) != RFX_OK) return rc;
+      TraceWork w;
+      w.sceneBlob = ctx->dBlob;
+      w.sceneBytes = ctx->blobBytes;
+      w.fp = ctx->snap;
+      w.fp.p0 = cur; w.fp.p1 = end; w.fp.firstRank = firstRank;
+      w.fp.seedRender = ctx->seedRender;
+      w.sampleStates = ctx->dSampleStates;
+      w.image = writeImage ? ctx->dImage : nullptr;
+      w.argbOut = argbOut;
+      w.sigOut = ctx->sigOn ? ctx->dSig : nullptr;
+      w.counters = ctx->dCounters;
+      cudaEvent_t evA = nullptr, evB = nullptr;
+      if (ctx->profiling)
+      {
+        if (ctx->evUsed + 2 > ctx->evPool.size())
+          for (int i = 0; i < 2; i++) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->evPool.push_back(e); }
+        evA = ctx->evPool[ctx->evUsed++]; evB = ctx->evPool[ctx->evUsed++];
+        CK(cudaEventRecord(evA, st));
+      }
+      ctx->stats.kernel_launches += launchTrace(w, st);
+      if (evB) CK(cudaEventRecord(evB, st));
+      CK(cudaGetLastError());
+      ctx->stats.samples += nCalls;
+      if (ctx->snap.jitter && sn > 0) ctx->seedRender = lcgJumpHost(ctx->seedRender, 2 * (end - cur));
+    }
+    cur = end;
+  }
+  return RFX_OK;
+}
+
+int checkStatus(rfx_ctx * ctx)
+{
+  int status = 0;
+  CK(cudaMemcpy(&status, ctx->dStatus, sizeof(int), cudaMemcpyDeviceToHost));
+  if (status) return fail(ctx, RFX_ERR_RNG, "random-stream ranking ran out of over-provisioned draws");
+  return RFX_OK;
+}
+
+} // namespace
+
+// =====================================================================================================================
+extern "C"
+{
+
+const char * rfx_version(void) { return "reflaxman_b200 0.1 (sm_100a)"; }
+
+int rfx_create(rfx_ctx ** out, int device)
+{
+  rfx_ctx * ctx = nullptr;   // for CK
+  if (!out) return fail(nullptr, RFX_ERR_ARG, "rfx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(nullptr, RFX_ERR_NODEV, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(nullptr, RFX_ERR_ARG, "rfx_create: bad device ordinal");
+  cudaDeviceProp prop;
+  CK(cudaSetDevice(device));
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, RFX_ERR_NODEV, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                ", this library carries sm_100a code only (there is no CPU fallback)");
+  ctx = new rfx_ctx();
+  ctx->device = device;
+  ctx->prop = prop;
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  memset(&ctx->snap, 0, sizeof(ctx->snap));
+  cudaError_t err = cudaSuccess;
+  auto step = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+  step(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  step(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  step(cudaMalloc((void **)&ctx->dRng, 2 * sizeof(uint32_t)));
+  step(cudaMalloc((void **)&ctx->dStatus, sizeof(int)));
+  step(cudaMalloc((void **)&ctx->dCounters, 64 * sizeof(unsigned long long)));
+  step(cudaMalloc((void **)&ctx->dLut, 256 * sizeof(float)));
+  for (int i = 0; i < 3; i++)
+  {
+    step(cudaEventCreateWithFlags(&ctx->evRendered[i], cudaEventDisableTiming));
+    step(cudaEventCreateWithFlags(&ctx->evCopied[i], cudaEventDisableTiming));
+  }
+  if (err == cudaSuccess)
+  {
+    float lut[256];
+    for (int i = 0; i < 256; i++) lut[i] = float(i) / 255.0f;   // Color(ARGB), Color.cpp:11-13
+    const uint32_t seeds[2] = { 12345u, 12345u };
+    step(cudaMemcpy(ctx->dLut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    step(cudaMemcpy(ctx->dRng, seeds, sizeof(seeds), cudaMemcpyHostToDevice));
+    step(cudaMemset(ctx->dStatus, 0, sizeof(int)));
+    step(cudaMemset(ctx->dCounters, 0, 64 * sizeof(unsigned long long)));
+  }
+  if (err != cudaSuccess)
+  {
+    std::string msg = std::string("rfx_create: ") + cudaGetErrorString(err);
+    rfx_destroy(ctx);
+    return fail(nullptr, RFX_ERR_CUDA, msg);
+  }
+  *out = ctx;
+  return RFX_OK;
+}
+
+void rfx_destroy(rfx_ctx * ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (HostTex & t : ctx->tex) if (t.dev) cudaFree(t.dev);
+  cudaFree(ctx->dBlob); cudaFree(ctx->dLut); cudaFree(ctx->dImage); cudaFree(ctx->dSig); cudaFree(ctx->dRng);
+  cudaFree(ctx->dBlockCounts); cudaFree(ctx->dBlockOffsets); cudaFree(ctx->dSampleStates); cudaFree(ctx->dStatus);
+  cudaFree(ctx->dCounters);
+  for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
+  for (int i = 0; i < 3; i++)
+  {
+    cudaFree(ctx->dFrame[i]);
+    if (ctx->evRendered[i]) cudaEventDestroy(ctx->evRendered[i]);
+    if (ctx->evCopied[i]) cudaEventDestroy(ctx->evCopied[i]);
+  }
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+  delete ctx;
+}
+
+const char * rfx_last_error(const rfx_ctx * ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+int rfx_get_device_info(const rfx_ctx * ctx, rfx_device_info * out)
+{
+  if (!ctx || !out) return RFX_ERR_ARG;
+  memset(out, 0, sizeof(*out));
+  out->device = ctx->device;
+  out->sm_count = ctx->prop.multiProcessorCount;
+  out->cc_major = ctx->prop.major; out->cc_minor = ctx->prop.minor;
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+  out->clock_khz = khz;
+  out->total_mem = ctx->prop.totalGlobalMem;
+  strncpy(out->name, ctx->prop.name, sizeof(out->name) - 1);
+  return RFX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------- scene
+int rfx_scene_reset(rfx_ctx * ctx, const float ambient_rgb[3], float ambient_power)
+{
+  if (!ctx || !ambient_rgb) return fail(ctx, RFX_ERR_ARG, "rfx_scene_reset: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  for (HostTex & t : ctx->tex) if (t.dev) cudaFree(t.dev);
+  ctx->tex.clear(); ctx->objs.clear(); ctx->lights.clear();
+  ctx->skyTex = -1;
+  for (int i = 0; i < 3; i++)
+  {
+    ctx->ambient[i] = ambient_rgb[i];
+    ctx->env[i] = ambient_rgb[i] * ambient_power;   // envColor(diffLightColor * diffLightPower), Scene.cpp:12
+  }
+  ctx->ambientPower = ambient_power;
+  ctx->sceneDirty = true;
+  return RFX_OK;
+}
+
+int rfx_add_light(rfx_ctx * ctx, const float o[3], float radius, const float rgb[3], float power)
+{
+  if (!ctx || !o || !rgb) return fail(ctx, RFX_ERR_ARG, "rfx_add_light: NULL argument");
+  if (radius <= VSN) radius = VSN;                              // Scene.cpp:51-52
+  for (int i = 0; i < 3; i++) ctx->env[i] = ctx->env[i] + rgb[i] * power;   // envColor += color * power, Scene.cpp:54
+  Light l;
+  l.ox = o[0]; l.oy = o[1]; l.oz = o[2]; l.radius = radius;
+  l.r = rgb[0]; l.g = rgb[1]; l.b = rgb[2];
+  l.power = clampf(power, 0.0f, 1.0f);                          // OmniLight.cpp:13
+  ctx->lights.push_back(l);
+  ctx->sceneDirty = true;
+  return (int)ctx->lights.size() - 1;
+}
+
+int rfx_add_sphere(rfx_ctx * ctx, const float c[3], float radius, int mtype, const float rgb[3], float refl, float transp)
+{
+  if (!ctx || !c || !rgb) return fail(ctx, RFX_ERR_ARG, "rfx_add_sphere: NULL argument");
+  if (radius <= VSN) radius = VSN;                              // Scene.cpp:33-34
+  HostObj o;
+  memset(&o, 0, sizeof(o));
+  o.kind = 0;
+  o.mat = makeMaterial(mtype, rgb, refl, transp, (int)ctx->objs.size());
+  o.center[0] = c[0]; o.center[1] = c[1]; o.center[2] = c[2];
+  o.sqRadius = radius * radius;                                 // Sphere.cpp:19
+  ctx->objs.push_back(o);
+  ctx->sceneDirty = true;
+  return (int)ctx->objs.size() - 1;
+}
+
+int rfx_add_triangle(rfx_ctx * ctx, const float v[9], int mtype, const float rgb[3], float refl, float transp)
+{
+  if (!ctx || !v || !rgb) return fail(ctx, RFX_ERR_ARG, "rfx_add_triangle: NULL argument");
+  HostObj o;
+  memset(&o, 0, sizeof(o));
+  o.kind = 1;
+  o.mat = makeMaterial(mtype, rgb, refl, transp, (int)ctx->objs.size());
+  const H3 v0 = { v[0], v[1], v[2] }, v1 = { v[3], v[4], v[5] }, v2 = { v[6], v[7], v[8] };
+  const H3 n = hnormalize(hcross(hsub(v1, v0), hsub(v2, v0)));  // Triangle.cpp:13
+  const H3 nn = { -n.x, -n.y, -n.z };
+  invertColumns(hsub(v2, v0), hsub(v1, v0), nn, o.tri.ax);      // Triangle.cpp:19-20
+  o.tri.v0[0] = v0.x; o.tri.v0[1] = v0.y; o.tri.v0[2] = v0.z;
+  o.tri.n[0] = n.x; o.tri.n[1] = n.y; o.tri.n[2] = n.z;
+  ctx->objs.push_back(o);
+  ctx->sceneDirty = true;
+  return (int)ctx->objs.size() - 1;
+}
+
+int rfx_set_triangle_texture(rfx_ctx * ctx, int object, int texture, const float uv[6])
+{
+  if (!ctx || !uv) return fail(ctx, RFX_ERR_ARG, "rfx_set_triangle_texture: NULL argument");
+  if (object < 0 || object >= (int)ctx->objs.size() || ctx->objs[object].kind != 1)
+    return fail(ctx, RFX_ERR_ARG, "rfx_set_triangle_texture: object is not a triangle");
+  if (texture < 0 || texture >= (int)ctx->tex.size()) return fail(ctx, RFX_ERR_ARG, "rfx_set_triangle_texture: unknown texture");
+  HostObj & o = ctx->objs[object];
+  // tuvTrans = Matrix33(v3 - v1, v2 - v1, (0,0,-1)) with v_i = (tu_i, tv_i, 0), Triangle.cpp:116-119
+  o.tri.tuv[0] = uv[4] - uv[0]; o.tri.tuv[1] = uv[2] - uv[0];
+  o.tri.tuv[2] = uv[5] - uv[1]; o.tri.tuv[3] = uv[3] - uv[1];
+  o.tri.tu0 = uv[0]; o.tri.tv0 = uv[1];
+  o.mat.tex = texture;
+  ctx->sceneDirty = true;
+  return RFX_OK;
+}
+
+int rfx_add_plane(rfx_ctx * ctx, const float pos[3], const float norm[3], int mtype, const float rgb[3], float refl, float transp)
+{
+  if (!ctx || !pos || !norm || !rgb) return fail(ctx, RFX_ERR_ARG, "rfx_add_plane: NULL argument");
+  HostObj o;
+  memset(&o, 0, sizeof(o));
+  o.kind = 2;
+  o.mat = makeMaterial(mtype, rgb, refl, transp, (int)ctx->objs.size());
+  memcpy(o.plane.pos, pos, sizeof(float) * 3);
+  memcpy(o.plane.n, norm, sizeof(float) * 3);
+  ctx->objs.push_back(o);
+  ctx->sceneDirty = true;
+  return (int)ctx->objs.size() - 1;
+}
+
+int rfx_add_texture_argb(rfx_ctx * ctx, uint32_t w, uint32_t h, const uint32_t * argb)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  HostTex t;
+  if (argb && w && h)
+  {
+    t.w = w; t.h = h;
+    t.px.assign(argb, argb + (size_t)w * h);
+  }
+  ctx->tex.push_back(std::move(t));
+  ctx->sceneDirty = true;
+  return (int)ctx->tex.size() - 1;
+}
+
+int rfx_set_skybox(rfx_ctx * ctx, int texture)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  if (texture >= (int)ctx->tex.size()) return fail(ctx, RFX_ERR_ARG, "rfx_set_skybox: unknown texture");
+  // Skybox::loadTexture returns false and keeps the checker when the file failed to load (Skybox.cpp:30-36)
+  ctx->skyTex = (texture >= 0 && !ctx->tex[texture].px.empty()) ? texture : -1;
+  ctx->sceneDirty = true;
+  return ctx->skyTex >= 0 ? 1 : 0;
+}
+
+// --------------------------------------------------------------------------------------------------------- camera
+int rfx_set_camera(rfx_ctx * ctx, const float eye[3], const float view[9], float fov)
+{
+  if (!ctx || !eye || !view) return fail(ctx, RFX_ERR_ARG, "rfx_set_camera: NULL argument");
+  memcpy(ctx->eye, eye, sizeof(float) * 3);
+  memcpy(ctx->view, view, sizeof(float) * 9);
+  ctx->fov = fov;
+  return RFX_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------- seeds
+int rfx_set_seeds(rfx_ctx * ctx, uint32_t seed_vector3, uint32_t seed_render)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(ctx->dRng + ctx->rngSlot, &seed_vector3, sizeof(uint32_t), cudaMemcpyHostToDevice));
+  ctx->seedRender = seed_render;
+  return RFX_OK;
+}
+
+int rfx_get_seeds(rfx_ctx * ctx, uint32_t out[2])
+{
+  if (!ctx || !out) return RFX_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(&out[0], ctx->dRng + ctx->rngSlot, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  out[1] = ctx->seedRender;
+  return checkStatus(ctx);
+}
+
+int rfx_skip_samples(rfx_ctx * ctx, uint64_t n)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = useStream(ctx, ctx->stream)) != RFX_OK) return rc;
+  const uint64_t chunk = 1ull << 28;
+  while (n > 0)
+  {
+    const uint64_t m = std::min(n, chunk);
+    if ((rc = rankSamples(ctx, m, true, ctx->stream)) != RFX_OK) return rc;
+    n -= m;
+  }
+  return RFX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------- Render
+int rfx_set_image_size(rfx_ctx * ctx, uint32_t width, uint32_t height)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  if (!width || !height) return fail(ctx, RFX_ERR_ARG, "rfx_set_image_size: zero size");   // Render.cpp:59-62: ignored
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = useStream(ctx, ctx->stream)) != RFX_OK) return rc;
+  const size_t n = (size_t)width * height;
+  if ((rc = ensure(ctx, ctx->dImage, ctx->imageCap, n * 3)) != RFX_OK) return rc;
+  ctx->stats.kernel_launches += launchClear(ctx->dImage, n * 3, ctx->stream);   // Render.cpp:67-71
+  CK(cudaGetLastError());
+  ctx->W = width; ctx->H = height;
+  ctx->additiveCounter = 0;
+  ctx->inProgress = false;
+  ctx->cursor = 0;
+  return RFX_OK;
+}
+
+int rfx_render_begin(rfx_ctx * ctx, int reflect_num, int sample_num, int additive)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  if (reflect_num <= 0 || sample_num == 0) return fail(ctx, RFX_ERR_ARG, "rfx_render_begin: reflect_num must be > 0 and sample_num != 0");
+  if (!ctx->W || !ctx->H) return fail(ctx, RFX_ERR_ARG, "rfx_render_begin: image size not set");
+  if (sample_num > 1024 || sample_num < -4096) return fail(ctx, RFX_ERR_ARG, "rfx_render_begin: sample_num out of range");
+  ctx->reflNum = reflect_num;
+  ctx->sampleNum = sample_num;
+  ctx->additive = additive != 0;
+  ctx->inProgress = true;
+  ctx->cursor = 0;
+  if (additive) ctx->additiveCounter++; else ctx->additiveCounter = 0;     // Render.cpp:130-133
+
+  FrameParams & fp = ctx->snap;
+  memset(&fp, 0, sizeof(fp));
+  memcpy(fp.eye, ctx->eye, sizeof(fp.eye));      // renderCameraEye / renderCameraView snapshot, Render.cpp:125-126
+  memcpy(fp.view, ctx->view, sizeof(fp.view));
+  // Render.cpp:148-150.  NOTE the reference evaluates rz with the LIVE camera.fov inside renderNext; Pulse never changes
+  // fov (Camera.cpp has no writer besides the constructors), so latching it here is equivalent.
+  fp.rz = float(ctx->W) / 2.0f / tanf(ctx->fov / 2.0f);
+  fp.wHalf = ctx->W / 2.0f;
+  fp.hHalf = ctx->H / 2.0f;
+  fp.W = ctx->W; fp.H = ctx->H;
+  fp.reflNum = reflect_num;
+  fp.sampleNum = sample_num;
+  fp.jitter = additive ? 1 : 0;
+  fp.accumulate = ctx->additiveCounter > 1 ? 1 : 0;
+  return RFX_OK;
+}
+
+int rfx_render_next(rfx_ctx * ctx, uint32_t pixels)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  const uint64_t total = (uint64_t)ctx->W * ctx->H;
+  if (!pixels || !ctx->inProgress || ctx->cursor >= total) return 0;     // Render.cpp:143-144: returns false
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = useStream(ctx, ctx->stream)) != RFX_OK) return rc;
+  if ((rc = uploadScene(ctx, ctx->stream)) != RFX_OK) return rc;
+  if (ctx->sigOn && (rc = ensure(ctx, ctx->dSig, ctx->sigCap, (size_t)total)) != RFX_OK) return rc;
+  const uint64_t end = std::min(total, ctx->cursor + pixels);
+  if ((rc = renderRange(ctx, ctx->cursor, end, nullptr, true, ctx->stream)) != RFX_OK) return rc;
+  ctx->cursor = end;
+  if (ctx->cursor >= total) ctx->inProgress = false;                     // Render.cpp:207-211
+  return ctx->inProgress ? 1 : 0;
+}
+
+float rfx_progress(const rfx_ctx * ctx)
+{
+  if (!ctx || !ctx->W || !ctx->H) return 0.0f;
+  // float(curx + cury * imageWidth) * 100.0f / imageWidth / imageHeight, Render.cpp:223-226; a finished frame leaves the
+  // cursor at (0, imageHeight) upstream, i.e. 100 %
+  return float(ctx->cursor) * 100.0f / ctx->W / ctx->H;
+}
+
+int rfx_additive_counter(const rfx_ctx * ctx) { return ctx ? ctx->additiveCounter : 0; }
+int rfx_in_progress(const rfx_ctx * ctx) { return ctx && ctx->inProgress ? 1 : 0; }
+
+static int readResolved(rfx_ctx * ctx, float * rgbf, uint32_t * argb)
+{
+  if (!ctx->W || !ctx->H) return fail(ctx, RFX_ERR_ARG, "image size not set");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = useStream(ctx, ctx->stream)) != RFX_OK) return rc;
+  const size_t n = (size_t)ctx->W * ctx->H;
+  if (argb)
+  {
+    if ((rc = ensure(ctx, ctx->dFrame[0], ctx->frameCap, n)) != RFX_OK) return rc;
+    ctx->stats.kernel_launches += launchResolve(ctx->dImage, n, ctx->additiveCounter, nullptr, ctx->dFrame[0], ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(argb, ctx->dFrame[0], n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += n * 4;
+  }
+  if (rgbf)
+  {
+    if (ctx->additiveCounter > 1)
+    {
+      // divide on the device into the ranked-state scratch (reused as a float buffer), then copy
+      size_t need = n * 3;
+      if ((rc = ensure(ctx, ctx->dSampleStates, ctx->statesCap, need)) != RFX_OK) return rc;
+      ctx->stats.kernel_launches += launchResolve(ctx->dImage, n, ctx->additiveCounter, reinterpret_cast<float *>(ctx->dSampleStates), nullptr, ctx->stream);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(rgbf, ctx->dSampleStates, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    else
+      CK(cudaMemcpyAsync(rgbf, ctx->dImage, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += n * 12;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return checkStatus(ctx);
+}
+
+int rfx_read_argb(rfx_ctx * ctx, uint32_t * dst)
+{
+  if (!ctx || !dst) return fail(ctx, RFX_ERR_ARG, "rfx_read_argb: NULL argument");
+  return readResolved(ctx, nullptr, dst);
+}
+
+int rfx_read_rgbf(rfx_ctx * ctx, float * dst)
+{
+  if (!ctx || !dst) return fail(ctx, RFX_ERR_ARG, "rfx_read_rgbf: NULL argument");
+  return readResolved(ctx, dst, nullptr);
+}
+
+int rfx_read_pixel(rfx_ctx * ctx, int x, int y, float rgb[3])
+{
+  if (!ctx || !rgb) return RFX_ERR_ARG;
+  rgb[0] = rgb[1] = rgb[2] = 0.0f;                                        // Render.cpp:112-113
+  if (x < 0 || y < 0 || (uint32_t)x >= ctx->W || (uint32_t)y >= ctx->H) return RFX_OK;
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = useStream(ctx, ctx->stream)) != RFX_OK) return rc;
+  CK(cudaMemcpyAsync(rgb, ctx->dImage + ((size_t)y * ctx->W + x) * 3, 12, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.d2h_bytes += 12;
+  if (ctx->additiveCounter > 1)
+  {
+    const float d = float(ctx->additiveCounter);                         // Render.cpp:109-110, Color.cpp:99-107
+    rgb[0] = rgb[0] / d; rgb[1] = rgb[1] / d; rgb[2] = rgb[2] / d;
+  }
+  return RFX_OK;
+}
+
+int rfx_enable_signatures(rfx_ctx * ctx, int on)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  ctx->sigOn = on != 0;
+  return RFX_OK;
+}
+
+int rfx_read_signatures(rfx_ctx * ctx, uint32_t * dst)
+{
+  if (!ctx || !dst) return RFX_ERR_ARG;
+  if (!ctx->sigOn || !ctx->dSig) return fail(ctx, RFX_ERR_ARG, "rfx_read_signatures: signatures are not enabled");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = useStream(ctx, ctx->stream)) != RFX_OK) return rc;
+  CK(cudaMemcpyAsync(dst, ctx->dSig, (size_t)ctx->W * ctx->H * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RFX_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------- batch path
+static int beginFrame(rfx_ctx * ctx, const float * cam, int reflect_num, int sample_num)
+{
+  int rc;
+  if ((rc = rfx_set_camera(ctx, cam, cam + 3, cam[12])) != RFX_OK) return rc;
+  ctx->additiveCounter = 0;   // each frame is a fresh setImageSize-sized, non-additive screenshot render (Pulse.cpp:174-176)
+  return rfx_render_begin(ctx, reflect_num, sample_num, 0);
+}
+
+int rfx_render_frames_device(rfx_ctx * ctx, int n_frames, const float * cams, int reflect_num, int sample_num,
+                             uint32_t * argb_device, void * stream)
+{
+  if (!ctx || !cams || !argb_device || n_frames < 0) return fail(ctx, RFX_ERR_ARG, "rfx_render_frames_device: bad argument");
+  if (!ctx->W || !ctx->H) return fail(ctx, RFX_ERR_ARG, "rfx_render_frames_device: image size not set");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  int rc;
+  if ((rc = useStream(ctx, st)) != RFX_OK) return rc;
+  if ((rc = uploadScene(ctx, st)) != RFX_OK) return rc;
+  const uint64_t total = (uint64_t)ctx->W * ctx->H;
+  for (int f = 0; f < n_frames; f++)
+  {
+    if ((rc = beginFrame(ctx, cams + 13 * (size_t)f, reflect_num, sample_num)) != RFX_OK) return rc;
+    if ((rc = renderRange(ctx, 0, total, argb_device + (size_t)f * total, false, st)) != RFX_OK) return rc;
+    ctx->cursor = total;
+    ctx->inProgress = false;
+  }
+  return RFX_OK;
+}
+
+int rfx_render_frames(rfx_ctx * ctx, int n_frames, const float * cams, int reflect_num, int sample_num, uint32_t * argb_host)
+{
+  if (!ctx || !cams || !argb_host || n_frames < 0) return fail(ctx, RFX_ERR_ARG, "rfx_render_frames: bad argument");
+  if (!ctx->W || !ctx->H) return fail(ctx, RFX_ERR_ARG, "rfx_render_frames: image size not set");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int rc;
+  if ((rc = useStream(ctx, st)) != RFX_OK) return rc;
+  if ((rc = uploadScene(ctx, st)) != RFX_OK) return rc;
+  const uint64_t total = (uint64_t)ctx->W * ctx->H;
+  // three device frame slots: render frame f into slot f%3 on the compute stream while the copy stream drains older slots
+  for (int i = 0; i < 3; i++)
+  {
+    size_t cap = ctx->dFrame[i] ? ctx->frameCap : 0;
+    if (cap < total)
+    {
+      CK(cudaDeviceSynchronize());
+      for (int j = 0; j < 3; j++) { if (ctx->dFrame[j]) cudaFree(ctx->dFrame[j]); ctx->dFrame[j] = nullptr; }
+      for (int j = 0; j < 3; j++) CK(cudaMalloc((void **)&ctx->dFrame[j], total * 4));
+      ctx->frameCap = total;
+      break;
+    }
+  }
+  for (int f = 0; f < n_frames; f++)
+  {
+    const int slot = f % 3;
+    if (f >= 3) CK(cudaStreamWaitEvent(st, ctx->evCopied[slot], 0));   // slot free again?
+    if ((rc = beginFrame(ctx, cams + 13 * (size_t)f, reflect_num, sample_num)) != RFX_OK) return rc;
+    if ((rc = renderRange(ctx, 0, total, ctx->dFrame[slot], false, st)) != RFX_OK) return rc;
+    ctx->cursor = total;
+    ctx->inProgress = false;
+    CK(cudaEventRecord(ctx->evRendered[slot], st));
+    CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evRendered[slot], 0));
+    CK(cudaMemcpyAsync(argb_host + (size_t)f * total, ctx->dFrame[slot], total * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
+    CK(cudaEventRecord(ctx->evCopied[slot], ctx->copyStream));
+    ctx->stats.d2h_bytes += total * 4;
+  }
+  CK(cudaStreamSynchronize(ctx->copyStream));
+  CK(cudaStreamSynchronize(st));
+  return checkStatus(ctx);
+}
+
+int rfx_synchronize(rfx_ctx * ctx)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->lastStream) CK(cudaStreamSynchronize(ctx->lastStream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return checkStatus(ctx);
+}
+
+// ----------------------------------------------------------------------------------------------------------- stats
+int rfx_get_stats(rfx_ctx * ctx, rfx_stats * out)
+{
+  if (!ctx || !out) return RFX_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  unsigned long long c[64];
+  CK(cudaMemcpy(c, ctx->dCounters, sizeof(c), cudaMemcpyDeviceToHost));
+  uint64_t b = 0, s = 0;
+  for (int i = 0; i < 32; i++) { b += c[2 * i]; s += c[2 * i + 1]; }
+  ctx->stats.bounces = b;
+  ctx->stats.shadow_rays = s;
+  ctx->stats.rays = b + s;
+  for (size_t i = 0; i + 1 < ctx->evUsed; i += 2)
+  {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->evPool[i], ctx->evPool[i + 1]));
+    ctx->stats.trace_kernel_ms += ms;
+    ctx->stats.trace_kernels++;
+  }
+  ctx->evUsed = 0;
+  *out = ctx->stats;
+  return RFX_OK;
+}
+
+int rfx_stats_reset(rfx_ctx * ctx)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemset(ctx->dCounters, 0, 64 * sizeof(unsigned long long)));
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->evUsed = 0;
+  return RFX_OK;
+}
+
+int rfx_enable_profiling(rfx_ctx * ctx, int on)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  ctx->profiling = on != 0;
+  return RFX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,762 @@
+// rfx_kernels.cu — hand-written sm_100a kernels for ReflaxMan's per-pixel trace-and-shade path.
+//
+//   K1  k_rng_count / k_rng_scan / k_rng_scatter   the serial rejection-sampled LCG stream, ranked in parallel
+//   K2  k_trace                                     primary rays + bounded bounce loop + shadow rays + shading + textures
+//   K3  k_resolve                                   imagePixel() divide + 8-bit ARGB pack
+//
+// ARITHMETIC CONTRACT.  This file is compiled with --fmad=false and without any fast-math flag: every + - * below
+// is an IEEE-754 binary32 round-to-nearest operation that ptxas may not fuse, / is div.rn, sqrtf is sqrt.rn, and
+// denormals are kept.  Expressions are parenthesised in the order the reference's overloaded C++ operators evaluate
+// them, because a last-bit difference in the geometry chain flips hit decisions of grazing
+// rays and checker/texel boundaries into differences of tens of LSB.  The only arithmetic allowed
+// to differ from the reference's glibc build is powf (two sites, colour only).
+//
+// Reference map (path:line under /root/reference/src/common):
+//   rngAccept, k_rng_*          Vector3.cpp:176-188, trace_math.h:34-39
+//   sphere tests                Sphere.cpp:44-85
+//   triangle tests              Triangle.cpp:53-108 (setup Triangle.cpp:11-21,110-120 happens on the host)
+//   plane tests                 Plane.cpp:36-73
+//   reflectVec / normalizeVec   trace_math.cpp:3-23, Vector3.cpp:55-64,143-151
+//   texSample                   Texture.cpp:216-269, Color.cpp:9-14
+//   skySample                   Skybox.cpp:39-106
+//   traceSample                 Scene.cpp:73-236
+//   k_trace pixel loop          Render.cpp:136-215
+//   k_resolve                   Render.cpp:103-114, Color.cpp:114-117
+#include "rfx_kernels.h"
+#include <float.h>
+#include <math.h>
+
+namespace rfx
+{
+
+#define RFX_VSN 1.08420217248550443e-19f   // sqrtf(FLT_MIN) = 2^-63, reference trace_math.h:17
+#define RFX_DELTA 0.0001f                  // reference trace_math.h:18
+
+// =====================================================================================================================
+// LCG (reference trace_math.h:36-39): g = 214013*g + 2531011 (mod 2^32), draw = (g >> 16) & 0x7FFF
+// =====================================================================================================================
+__host__ __device__ __forceinline__ uint32_t lcgJump(uint32_t s, uint32_t n)
+{
+  // f^n for the affine map f(s) = A s + C by binary powering; the period divides 2^32 so n mod 2^32 is exact
+  uint32_t A = 214013u, C = 2531011u;
+  while (n)
+  {
+    if (n & 1u) s = A * s + C;
+    C = C * (A + 1u);
+    A = A * A;
+    n >>= 1;
+  }
+  return s;
+}
+
+uint32_t lcgJumpHost(uint32_t s, uint64_t n) { return lcgJump(s, (uint32_t)n); }
+
+__device__ __forceinline__ float lcgDrawUnit(uint32_t & s)
+{
+  s = 214013u * s + 2531011u;
+  const int r = (int)((s >> 16) & 0x7FFFu);
+  return float(r) / 16383.5f - 1.f;   // float(fastrand()) / (float(FAST_RAND_MAX) / 2) - 1.f, Vector3.cpp:182-184
+}
+
+// one draw-triple: advances s by three draws; true when the candidate lies inside the unit sphere (Vector3.cpp:185)
+__device__ __forceinline__ bool rngTriple(uint32_t & s, float & x, float & y, float & z)
+{
+  x = lcgDrawUnit(s);
+  y = lcgDrawUnit(s);
+  z = lcgDrawUnit(s);
+  return !((x * x + y * y) + z * z > 1.f);
+}
+
+__global__ void __launch_bounds__(RNG_THREADS) k_rng_count(const uint32_t * __restrict__ stateIn, uint32_t * __restrict__ blockCounts)
+{
+  __shared__ int warpSums[RNG_THREADS / 32];
+  const uint32_t gid = blockIdx.x * RNG_THREADS + threadIdx.x;
+  uint32_t s = lcgJump(*stateIn, gid * (3u * RNG_TRIPLES_PER_THREAD));
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < RNG_TRIPLES_PER_THREAD; k++)
+  {
+    float x, y, z;
+    cnt += rngTriple(s, x, y, z) ? 1 : 0;
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < RNG_THREADS / 32; w++) t += warpSums[w];
+    blockCounts[blockIdx.x] = (uint32_t)t;
+  }
+}
+
+// single-CTA exclusive scan of the per-block accept counts (a few thousand to a few hundred thousand entries)
+__global__ void __launch_bounds__(1024) k_rng_scan(const uint32_t * __restrict__ counts, uint32_t * __restrict__ offsets,
+                                                   uint32_t nBlocks, unsigned long long n, int * status)
+{
+  __shared__ unsigned long long part[1024];
+  const uint32_t per = (nBlocks + 1023u) / 1024u;
+  const uint32_t b0 = threadIdx.x * per;
+  const uint32_t b1 = min(b0 + per, nBlocks);
+  unsigned long long sum = 0;
+  for (uint32_t b = b0; b < b1; b++) sum += counts[b];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials
+  for (int off = 1; off < 1024; off <<= 1)
+  {
+    unsigned long long v = (threadIdx.x >= off) ? part[threadIdx.x - off] : 0ull;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned long long run = part[threadIdx.x] - sum;
+  for (uint32_t b = b0; b < b1; b++)
+  {
+    // offsets saturate at 2^32-1: any block whose offset is >= n is skipped by the scatter pass anyway
+    offsets[b] = run > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)run;
+    run += counts[b];
+  }
+  if (threadIdx.x == 1023 && part[1023] < n) *status = 1;
+}
+
+__global__ void __launch_bounds__(RNG_THREADS) k_rng_scatter(const uint32_t * __restrict__ stateIn, uint32_t * __restrict__ stateOut,
+                                                             const uint32_t * __restrict__ blockOffsets,
+                                                             uint32_t * __restrict__ sampleStates, unsigned long long n, uint32_t rankBase)
+{
+  __shared__ int warpSums[RNG_THREADS / 32];
+  const unsigned long long boff = (unsigned long long)blockOffsets[blockIdx.x] + rankBase;
+  if (boff >= n) return;   // uniform per CTA
+
+  const uint32_t gid = blockIdx.x * RNG_THREADS + threadIdx.x;
+  const uint32_t sStart = lcgJump(*stateIn, gid * (3u * RNG_TRIPLES_PER_THREAD));
+  uint32_t s = sStart;
+  uint32_t mask = 0;
+#pragma unroll
+  for (int k = 0; k < RNG_TRIPLES_PER_THREAD; k++)
+  {
+    float x, y, z;
+    if (rngTriple(s, x, y, z)) mask |= 1u << k;
+  }
+  const int cnt = __popc(mask);
+  // block-wide exclusive scan of cnt
+  int incl = cnt;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1)
+  {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if ((threadIdx.x & 31) >= off) incl += v;
+  }
+  if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  int wbase = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); w++) wbase += warpSums[w];
+  unsigned long long rank = boff + (unsigned long long)(wbase + incl - cnt);
+
+  s = sStart;
+#pragma unroll
+  for (int k = 0; k < RNG_TRIPLES_PER_THREAD; k++)
+  {
+    const uint32_t before = s;
+    s = 214013u * s + 2531011u;
+    s = 214013u * s + 2531011u;
+    s = 214013u * s + 2531011u;
+    if (mask & (1u << k))
+    {
+      if (rank < n)
+      {
+        if (sampleStates) sampleStates[rank] = before;
+        if (rank == n - 1) *stateOut = s;
+      }
+      rank++;
+    }
+  }
+}
+
+uint32_t rngBlocksFor(uint64_t n)
+{
+  // acceptance is pi/6 = 0.5236 (1.91 triples per sample); 2n + 4096 triples leaves > 7 sigma of slack for every n
+  const uint64_t triples = 2 * n + 4096;
+  return (uint32_t)((triples + RNG_TRIPLES_PER_BLOCK - 1) / RNG_TRIPLES_PER_BLOCK);
+}
+
+int launchRngRank(const RngWork & w, cudaStream_t st)
+{
+  k_rng_count<<<w.nBlocks, RNG_THREADS, 0, st>>>(w.stateIn, w.blockCounts);
+  k_rng_scan<<<1, 1024, 0, st>>>(w.blockCounts, w.blockOffsets, w.nBlocks, (unsigned long long)w.n, w.status);
+  k_rng_scatter<<<w.nBlocks, RNG_THREADS, 0, st>>>(w.stateIn, w.stateOut, w.blockOffsets, w.sampleStates, (unsigned long long)w.n, 0u);
+  return 3;
+}
+
+// =====================================================================================================================
+// vector helpers (float3 by value; un-contracted, reference evaluation order)
+// =====================================================================================================================
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }
+__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 vscale(V3 a, float f) { return mk(a.x * f, a.y * f, a.z * f); }
+__device__ __forceinline__ float vdot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }       // Vector3.cpp:124-127
+__device__ __forceinline__ float vsqlen(V3 a) { return (a.x * a.x + a.y * a.y) + a.z * a.z; }           // Vector3.cpp:41-44
+__device__ __forceinline__ float vlen(V3 a) { return sqrtf(vsqlen(a)); }                                // Vector3.cpp:36-39
+__device__ __forceinline__ V3 normalizeVec(V3 a)   // Vector3.cpp:55-64 == trace_math.cpp:3-12: three true divides, guarded
+{
+  const float l = vlen(a);
+  if (l > RFX_VSN) return mk(a.x / l, a.y / l, a.z / l);
+  return a;
+}
+__device__ __forceinline__ V3 reflectVec(V3 v, V3 n)   // trace_math.cpp:14-23: v - (2*n) * ((v.n)/(n.n))
+{
+  const float dn = vdot(n, n);
+  if (dn > RFX_VSN)
+  {
+    const float s = vdot(v, n) / dn;
+    return mk(v.x - (n.x * 2.0f) * s, v.y - (n.y * 2.0f) * s, v.z - (n.z * 2.0f) * s);
+  }
+  return v;
+}
+__device__ __forceinline__ float clamp01(float v) { return v < 0.0f ? 0.0f : v > 1.0f ? 1.0f : v; }   // trace_math.h:24
+
+// =====================================================================================================================
+// scene view over the shared-memory copy of the blob
+// =====================================================================================================================
+struct SceneView
+{
+  const SceneHeader * h;
+  const Light * lights;
+  const float4 * spheres;
+  const Triangle * tris;
+  const Plane * planes;
+  const Material * mats;
+  const TexRef * tex;
+};
+
+__device__ __forceinline__ SceneView makeView(const unsigned char * base)
+{
+  SceneView v;
+  v.h = reinterpret_cast<const SceneHeader *>(base);
+  v.lights = reinterpret_cast<const Light *>(base + v.h->offLights);
+  v.spheres = reinterpret_cast<const float4 *>(base + v.h->offSpheres);
+  v.tris = reinterpret_cast<const Triangle *>(base + v.h->offTris);
+  v.planes = reinterpret_cast<const Plane *>(base + v.h->offPlanes);
+  v.mats = reinterpret_cast<const Material *>(base + v.h->offMats);
+  v.tex = reinterpret_cast<const TexRef *>(base + v.h->offTex);
+  return v;
+}
+
+// =====================================================================================================================
+// textures (reference Texture.cpp:216-269) and skybox (Skybox.cpp:39-106)
+// =====================================================================================================================
+__device__ __forceinline__ V3 texel(const TexRef & t, const float * __restrict__ lut, uint32_t x, uint32_t y)
+{
+  const uint32_t c = __ldg(t.px + (x + t.w * y));
+  // Color(ARGB): float(byte) / 255.0f (Color.cpp:11-13) through the host-computed 256-entry table
+  return mk(__ldg(lut + ((c >> 16) & 0xFFu)), __ldg(lut + ((c >> 8) & 0xFFu)), __ldg(lut + (c & 0xFFu)));
+}
+
+__device__ V3 texSample(const SceneView & sc, int texId, float u, float v)
+{
+  if (u < 0.0f || u > 1.0f || v < 0.0f || v > 1.0f) return mk(0.0f, 0.0f, 0.0f);
+  const TexRef * t = texId >= 0 ? &sc.tex[texId] : nullptr;
+  if (!t || !t->px)
+  {
+    const float g = ((int(u * 50) % 2) ^ (int(v * 50) % 2)) ? 0.5f : 0.75f;   // Texture.cpp:243
+    return mk(g, g, g);
+  }
+  const float * lut = sc.h->byteLut;
+  const float cu = u < 0.0f ? 0.0f : u > (1.0f - FLT_EPSILON) ? (1.0f - FLT_EPSILON) : u;
+  const float cv = v < 0.0f ? 0.0f : v > (1.0f - FLT_EPSILON) ? (1.0f - FLT_EPSILON) : v;
+  const float fx = cu * float(t->w);
+  const float fy = cv * float(t->h);
+  const uint32_t x = (uint32_t)fx, y = (uint32_t)fy;
+  if (x < t->w - 1 && y < t->h - 1)
+  {
+    const V3 c00 = texel(*t, lut, x, y), c01 = texel(*t, lut, x, y + 1), c10 = texel(*t, lut, x + 1, y), c11 = texel(*t, lut, x + 1, y + 1);
+    const float uf = fx - floorf(fx), vf = fy - floorf(fy);
+    const float uo = 1 - uf, vo = 1 - vf;
+    // (c00*uo + c10*uf)*vo + (c01*uo + c11*uf)*vf, Texture.cpp:264
+    return mk((c00.x * uo + c10.x * uf) * vo + (c01.x * uo + c11.x * uf) * vf,
+              (c00.y * uo + c10.y * uf) * vo + (c01.y * uo + c11.y * uf) * vf,
+              (c00.z * uo + c10.z * uf) * vo + (c01.z * uo + c11.z * uf) * vf);
+  }
+  if (x >= t->w || y >= t->h) return mk(0.0f, 0.0f, 0.0f);   // Texture.cpp:223-224 (unreachable after the clamp)
+  return texel(*t, lut, x, y);
+}
+
+__device__ V3 skySample(const SceneView & sc, V3 ray)
+{
+  const float uLeft = 1.0f / 8.0f, vMid = 3.0f / 6.0f, uFront = 3.0f / 8.0f, uRight = 5.0f / 8.0f, uBack = 7.0f / 8.0f;
+  const float vTop = 5.0f / 6.0f, vBottom = 1.0f / 6.0f;
+  const V3 n = normalizeVec(ray);
+  const float x = n.x, y = n.y, z = n.z;
+  const float ax = fabsf(x) + RFX_VSN, ay = fabsf(y) + RFX_VSN, az = fabsf(z) + RFX_VSN;
+  const float hw = sc.h->halfTileW, hh = sc.h->halfTileH;
+  float u, v;
+  if (az >= ax && az >= ay)
+  {
+    if (z > 0) { u = uFront + x / az * hw; v = vMid + y / az * hh; }
+    else       { u = uBack - x / az * hw;  v = vMid + y / az * hh; }
+  }
+  else if (ax >= ay && ax >= az)
+  {
+    if (x > 0) { u = uRight - z / ax * hw; v = vMid + y / ax * hh; }
+    else       { u = uLeft + z / ax * hw;  v = vMid + y / ax * hh; }
+  }
+  else
+  {
+    if (y > 0) { u = uFront + x / ay * hw; v = vTop - z / ay * hh; }      // uTop == uFront == uBottom == 3/8
+    else       { u = uFront + x / ay * hw; v = vBottom + z / ay * hh; }
+  }
+  return texSample(sc, sc.h->skyTex, u, v);
+}
+
+// =====================================================================================================================
+// intersection: all objects against one ray.  ANYHIT = shadow query (reference passes NULL outputs).
+// Per-ray invariants of the sphere test (a, 2*ray, 4a, 2a) are hoisted: same operations, evaluated once.
+// =====================================================================================================================
+struct HitRec
+{
+  int idx;        // position in the sorted object arrays (spheres, triangles, planes), -1 = none
+  int order;      // insertion index (tie-break)
+  float dist;
+  float t;
+  float u, v;     // triangle barycentrics (texture lookup)
+};
+
+template <bool ANYHIT>
+__device__ __forceinline__ bool intersectAll(const SceneView & sc, V3 o, V3 d, int skipIdx, HitRec & best)
+{
+  const SceneHeader & h = *sc.h;
+  const float a = vsqlen(d);                         // Sphere.cpp:50
+  const float r2x = d.x * 2.0f, r2y = d.y * 2.0f, r2z = d.z * 2.0f;   // 2.0f * ray, Sphere.cpp:51
+  const float a4 = 4.0f * a, a2 = 2.0f * a;          // Sphere.cpp:53,57
+  const bool aOk = a > RFX_VSN;
+
+  for (int i = 0; i < h.nSpheres; i++)
+  {
+    const float4 s = sc.spheres[i];
+    const float vx = o.x - s.x, vy = o.y - s.y, vz = o.z - s.z;
+    const float b = (r2x * vx + r2y * vy) + r2z * vz;
+    const float c = ((vx * vx + vy * vy) + vz * vz) - s.w;
+    const float disc = b * b - a4 * c;
+    if (disc >= 0.0f && aOk && (!ANYHIT || i != skipIdx))
+    {
+      const float t = (-b - sqrtf(disc)) / a2;
+      if (t > RFX_VSN)
+      {
+        const float fx = d.x * t, fy = d.y * t, fz = d.z * t;
+        const float dist = sqrtf((fx * fx + fy * fy) + fz * fz);
+        if (dist > RFX_DELTA)
+        {
+          if (ANYHIT) return true;
+          const int order = sc.mats[i].order;
+          if (dist < best.dist || (dist == best.dist && order < best.order))
+          {
+            best.dist = dist; best.idx = i; best.order = order; best.t = t;
+          }
+        }
+      }
+    }
+  }
+
+  for (int k = 0; k < h.nTris; k++)
+  {
+    const int i = h.nSpheres + k;
+    if (ANYHIT && i == skipIdx) continue;
+    const Triangle & tr = sc.tris[k];
+    const float px = o.x - tr.v0[0], py = o.y - tr.v0[1], pz = o.z - tr.v0[2];
+    // third row first (the only part the early-outs need); rows are (x*m1 + y*m2) + z*m3, Matrix33.cpp:232-234
+    const float oz = (px * tr.ax[6] + py * tr.ax[7]) + pz * tr.ax[8];
+    const float rz = (d.x * tr.ax[6] + d.y * tr.ax[7]) + d.z * tr.ax[8];
+    if (fabsf(rz) > RFX_VSN)
+    {
+      const float t = -oz / rz;
+      if (t > RFX_VSN)
+      {
+        const float ox = (px * tr.ax[0] + py * tr.ax[1]) + pz * tr.ax[2];
+        const float rx = (d.x * tr.ax[0] + d.y * tr.ax[1]) + d.z * tr.ax[2];
+        const float oy = (px * tr.ax[3] + py * tr.ax[4]) + pz * tr.ax[5];
+        const float ry = (d.x * tr.ax[3] + d.y * tr.ax[4]) + d.z * tr.ax[5];
+        const float u = ox + t * rx;
+        const float v = oy + t * ry;
+        if (u >= 0.0f && v >= 0.0f && u + v < 1.0f)
+        {
+          const float fx = d.x * t, fy = d.y * t, fz = d.z * t;
+          const float sq = (fx * fx + fy * fy) + fz * fz;
+          if (sq > RFX_DELTA * RFX_DELTA)
+          {
+            if (ANYHIT) return true;
+            const float dist = sqrtf(sq);
+            const int order = sc.mats[i].order;
+            if (dist < best.dist || (dist == best.dist && order < best.order))
+            {
+              best.dist = dist; best.idx = i; best.order = order; best.t = t; best.u = u; best.v = v;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  for (int k = 0; k < h.nPlanes; k++)
+  {
+    const int i = h.nSpheres + h.nTris + k;
+    if (ANYHIT && i == skipIdx) continue;
+    const Plane & pl = sc.planes[k];
+    const V3 n = mk(pl.n[0], pl.n[1], pl.n[2]);
+    const V3 vop = mk(pl.pos[0] - o.x, pl.pos[1] - o.y, pl.pos[2] - o.z);
+    const float den = vdot(n, d);
+    if (fabsf(den) > RFX_VSN)
+    {
+      const float t = vdot(n, vop) / den;
+      if (t > RFX_VSN)
+      {
+        const float fx = d.x * t, fy = d.y * t, fz = d.z * t;
+        const float sq = (fx * fx + fy * fy) + fz * fz;
+        if (sq > RFX_DELTA * RFX_DELTA)
+        {
+          if (ANYHIT) return true;
+          const float dist = sqrtf(sq);
+          const int order = sc.mats[i].order;
+          if (dist < best.dist || (dist == best.dist && order < best.order))
+          {
+            best.dist = dist; best.idx = i; best.order = order; best.t = t;
+          }
+        }
+      }
+    }
+  }
+  return ANYHIT ? false : best.idx >= 0;
+}
+
+// =====================================================================================================================
+// Scene::trace (reference Scene.cpp:73-236)
+// =====================================================================================================================
+#define RFX_SIG(h, ev) ((h) = ((h) ^ (uint32_t)(ev)) * 16777619u)
+
+__device__ V3 traceSample(const SceneView & sc, V3 origin, V3 ray, int reflNumber, V3 randDir,
+                          uint32_t & nBounces, uint32_t & nShadow, uint32_t & sig)
+{
+  const SceneHeader & h = *sc.h;
+  V3 mul = mk(1.0f, 1.0f, 1.0f);
+  V3 pix = mk(0.0f, 0.0f, 0.0f);
+
+  for (int refl = 0; refl < reflNumber; ++refl)
+  {
+    HitRec hit;
+    hit.idx = -1; hit.order = 0x7FFFFFFF; hit.dist = FLT_MAX; hit.t = 0; hit.u = 0; hit.v = 0;
+    nBounces++;
+
+    if (intersectAll<false>(sc, origin, ray, -1, hit))
+    {
+      RFX_SIG(sig, hit.order + 1);
+      // outputs of the winning object's trace(): drop, norm, reflect, material
+      const V3 full = vscale(ray, hit.t);
+      const V3 drop = vadd(origin, full);
+      const Material m = sc.mats[hit.idx];
+      V3 norm, color = mk(m.r, m.g, m.b);
+      if (hit.idx < h.nSpheres)
+      {
+        const float4 s = sc.spheres[hit.idx];
+        norm = mk(drop.x - s.x, drop.y - s.y, drop.z - s.z);               // Sphere.cpp:67
+      }
+      else if (hit.idx < h.nSpheres + h.nTris)
+      {
+        const Triangle & tr = sc.tris[hit.idx - h.nSpheres];
+        norm = mk(tr.n[0], tr.n[1], tr.n[2]);
+        if (m.tex >= 0)
+        {
+          // tuvTrans * Vector3(u, v, 0): (u*_11 + v*_12) + 0*_13 with _13 == 0, Triangle.cpp:91
+          const float tx = (hit.u * tr.tuv[0] + hit.v * tr.tuv[1]) + 0.0f;
+          const float ty = (hit.u * tr.tuv[2] + hit.v * tr.tuv[3]) + 0.0f;
+          color = texSample(sc, m.tex, tr.tu0 + tx, tr.tv0 + ty);
+        }
+      }
+      else
+      {
+        const Plane & pl = sc.planes[hit.idx - h.nSpheres - h.nTris];
+        norm = mk(pl.n[0], pl.n[1], pl.n[2]);
+      }
+      const V3 reflect = reflectVec(full, norm);
+
+      const float rayLen = vlen(ray);
+      const float normLen = vlen(norm);
+      const float reflectLen = vlen(reflect);
+      V3 sumLight = mk(0.0f, 0.0f, 0.0f);
+      V3 sumSpec = mk(0.0f, 0.0f, 0.0f);
+
+      for (int li = 0; li < h.nLights; li++)
+      {
+        const Light L = sc.lights[li];
+        const V3 toLight = mk(L.ox - drop.x, L.oy - drop.y, L.oz - drop.z);
+        const float facing = vdot(toLight, norm);
+        if (facing > RFX_VSN)
+        {
+          const V3 sray = vadd(toLight, vscale(randDir, L.radius));        // Scene.cpp:129
+          nShadow++;
+          HitRec dummy;
+          const bool inShadow = intersectAll<true>(sc, drop, sray, hit.idx, dummy);
+          RFX_SIG(sig, 0x100 + 2 * li + (inShadow ? 1 : 0));
+
+          if (!inShadow)
+          {
+            const float toLightLen = vlen(toLight);
+            float a = toLightLen * normLen;
+            const float lightDropCos = (a > RFX_VSN) ? facing / a : 0.0f;
+            if (L.power > RFX_VSN)
+            {
+              sumLight.x = sumLight.x + (L.r * lightDropCos) * L.power;       // Scene.cpp:156
+              sumLight.y = sumLight.y + (L.g * lightDropCos) * L.power;
+              sumLight.z = sumLight.z + (L.b * lightDropCos) * L.power;
+            }
+            a = vsqlen(toLight);
+            const float larsc = (a > RFX_VSN) ? 1.0f - L.radius * L.radius / a : 0.0f;   // Scene.cpp:160
+            if (larsc > 0)
+            {
+              const V3 dtl = vadd(normalizeVec(toLight), vscale(randDir, 1.0f - m.reflectivity));
+              a = vlen(dtl) * reflectLen;
+              float rsc = (a > RFX_VSN) ? vdot(dtl, reflect) / a : 0.0f;
+              rsc = clamp01(rsc + (1.0f - sqrtf(larsc)));
+              if (rsc > RFX_VSN)
+              {
+                if (L.radius > RFX_VSN)
+                {
+                  const float sp = powf(rsc, 1 + 3 * m.reflectivity * toLightLen / L.radius) * m.reflectivity;   // Scene.cpp:175
+                  sumSpec.x = sumSpec.x + L.r * sp;
+                  sumSpec.y = sumSpec.y + L.g * sp;
+                  sumSpec.z = sumSpec.z + L.b * sp;
+                }
+              }
+            }
+          }
+        }
+      }
+
+      sumLight = mk(h.ambient[0] * h.ambientPower + sumLight.x, h.ambient[1] * h.ambientPower + sumLight.y,
+                    h.ambient[2] * h.ambientPower + sumLight.z);           // Scene.cpp:189
+
+      V3 fin;
+      if (m.type == 1)   // dielectric, Scene.cpp:192-203
+      {
+        const float a = rayLen * normLen;
+        const float cosA = (a > RFX_VSN) ? clamp01(((ray.x * -norm.x + ray.y * -norm.y) + ray.z * -norm.z) / a) : 0.0f;
+        const float rf = 0.2f + 0.8f * powf(1.0f - cosA, 3.0f);
+        const float k = 1.0f - rf;
+        fin = mk(((color.x * k) * sumLight.x + sumSpec.x) * mul.x, ((color.y * k) * sumLight.y + sumSpec.y) * mul.y,
+                 ((color.z * k) * sumLight.z + sumSpec.z) * mul.z);
+        mul = vscale(mul, rf);
+      }
+      else               // metal, Scene.cpp:204-214
+      {
+        const float rf = 0.8f;
+        const float k = 1.0f - rf;
+        fin = mk(((color.x * k) * sumLight.x + sumSpec.x) * mul.x, ((color.y * k) * sumLight.y + sumSpec.y) * mul.y,
+                 ((color.z * k) * sumLight.z + sumSpec.z) * mul.z);
+        mul = mk(mul.x * (color.x * rf), mul.y * (color.y * rf), mul.z * (color.z * rf));
+      }
+
+      pix = mk(clamp01(pix.x + fin.x), clamp01(pix.y + fin.y), clamp01(pix.z + fin.z));
+
+      if (mul.x < 0.01f && mul.y < 0.01f && mul.z < 0.01f) break;
+
+      origin = drop;
+      ray = vadd(normalizeVec(reflect), vscale(randDir, 1.0f - m.reflectivity));   // Scene.cpp:226
+    }
+    else
+    {
+      RFX_SIG(sig, 0xFFFF);
+      const V3 sky = skySample(sc, ray);
+      pix = mk(clamp01(pix.x + (mul.x * sky.x) * h.env[0]), clamp01(pix.y + (mul.y * sky.y) * h.env[1]),
+               clamp01(pix.z + (mul.z * sky.z) * h.env[2]));              // Scene.cpp:230-231
+      break;
+    }
+  }
+  return pix;
+}
+
+// =====================================================================================================================
+// K2: Render::renderNext slice (reference Render.cpp:136-215).  One thread per pixel of the slice (grid SSAA: the
+// thread walks its s*s samples in the reference's ssx, ssy order so the sum is formed in the same order), or one
+// thread per block origin in block-preview mode.
+// =====================================================================================================================
+constexpr int TRACE_THREADS = 128;
+
+__device__ __forceinline__ uint32_t packArgb(float r, float g, float b)   // Color::argb, Color.cpp:114-117
+{
+  return (((uint32_t)(unsigned char)(r * 255.999f)) << 16) | (((uint32_t)(unsigned char)(g * 255.999f)) << 8) |
+         ((uint32_t)(unsigned char)(b * 255.999f));
+}
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace(const unsigned char * __restrict__ sceneBlob, uint32_t sceneBytes,
+                                                         const __grid_constant__ FrameParams fp,
+                                                         const uint32_t * __restrict__ sampleStates, float * __restrict__ image,
+                                                         uint32_t * __restrict__ argbOut, uint32_t * __restrict__ sigOut,
+                                                         unsigned long long * __restrict__ counters)
+{
+  extern __shared__ uint4 smemBlob[];
+  {
+    const uint4 * src = reinterpret_cast<const uint4 *>(sceneBlob);
+    for (uint32_t i = threadIdx.x; i < sceneBytes / 16; i += blockDim.x) smemBlob[i] = src[i];
+  }
+  __syncthreads();
+  const SceneView sc = makeView(reinterpret_cast<const unsigned char *>(smemBlob));
+
+  uint32_t nBounces = 0, nShadow = 0;
+  const V3 eye = mk(fp.eye[0], fp.eye[1], fp.eye[2]);
+  const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+
+  if (fp.sampleNum > 0)
+  {
+    const uint64_t p = fp.p0 + gid;
+    if (p < fp.p1)
+    {
+      const uint32_t y = (uint32_t)(p / fp.W), x = (uint32_t)(p % fp.W);
+      const int sn = fp.sampleNum;
+      const float rx = float(x) - fp.wHalf;
+      const float ry = float(y) - fp.hHalf;
+      float rndx = 0, rndy = 0;
+      if (fp.jitter)
+      {
+        uint32_t s = lcgJump(fp.seedRender, (uint32_t)(2 * gid));      // two draws per pixel, Render.cpp:177-178
+        s = 214013u * s + 2531011u; rndx = float((int)((s >> 16) & 0x7FFFu)) / float(0x7FFF);
+        s = 214013u * s + 2531011u; rndy = float((int)((s >> 16) & 0x7FFFu)) / float(0x7FFF);
+      }
+      V3 fin = mk(0.0f, 0.0f, 0.0f);
+      uint32_t sig = 2166136261u;
+      const uint32_t * st = sampleStates + gid * (uint64_t)(sn * sn);
+      for (int ssx = 0; ssx < sn; ssx++)
+        for (int ssy = 0; ssy < sn; ssy++)
+        {
+          uint32_t s = *st++;
+          V3 rd;
+          rngTriple(s, rd.x, rd.y, rd.z);
+          const float px = (rx + float(ssx) / float(sn)) + rndx;           // Render.cpp:184
+          const float py = (ry + float(ssy) / float(sn)) + rndy;
+          const V3 ray = mk((px * fp.view[0] + py * fp.view[1]) + fp.rz * fp.view[2],
+                            (px * fp.view[3] + py * fp.view[4]) + fp.rz * fp.view[5],
+                            (px * fp.view[6] + py * fp.view[7]) + fp.rz * fp.view[8]);
+          const V3 c = traceSample(sc, eye, ray, fp.reflNum, rd, nBounces, nShadow, sig);
+          fin = vadd(fin, c);
+        }
+      const float sq = float(sn * sn);
+      if (fabsf(sq) > RFX_VSN) fin = mk(fin.x / sq, fin.y / sq, fin.z / sq);   // Color::operator/=, Color.cpp:50-61
+      if (image)
+      {
+        float * px = image + p * 3;
+        if (fp.accumulate) { px[0] = px[0] + fin.x; px[1] = px[1] + fin.y; px[2] = px[2] + fin.z; }
+        else { px[0] = fin.x; px[1] = fin.y; px[2] = fin.z; }
+      }
+      if (argbOut) argbOut[p] = packArgb(fin.x, fin.y, fin.z);
+      if (sigOut) sigOut[p] = sig;
+    }
+  }
+  else
+  {
+    // block preview, Render.cpp:158-173: gid enumerates block origins in scan order starting at rank fp.firstRank
+    const uint32_t a = (uint32_t)(-fp.sampleNum);
+    const uint32_t bw = (fp.W + a - 1) / a;
+    const uint64_t k = fp.firstRank + gid;
+    const uint32_t y = (uint32_t)(k / bw) * a, x = (uint32_t)(k % bw) * a;
+    const uint64_t p = (uint64_t)y * fp.W + x;
+    if (y < fp.H && p < fp.p1)
+    {
+      uint32_t s = sampleStates[gid];
+      V3 rd;
+      rngTriple(s, rd.x, rd.y, rd.z);
+      const float px = float(x) - fp.wHalf, py = float(y) - fp.hHalf;
+      const V3 ray = mk((px * fp.view[0] + py * fp.view[1]) + fp.rz * fp.view[2],
+                        (px * fp.view[3] + py * fp.view[4]) + fp.rz * fp.view[5],
+                        (px * fp.view[6] + py * fp.view[7]) + fp.rz * fp.view[8]);
+      uint32_t sig = 2166136261u;
+      const V3 c = traceSample(sc, eye, ray, fp.reflNum, rd, nBounces, nShadow, sig);
+      const uint32_t ex = min(x + a, fp.W), ey = min(y + a, fp.H);
+      for (uint32_t qy = y; qy < ey; qy++)
+        for (uint32_t qx = x; qx < ex; qx++)
+        {
+          const uint64_t q = (uint64_t)qy * fp.W + qx;
+          if (image) { image[q * 3] = c.x; image[q * 3 + 1] = c.y; image[q * 3 + 2] = c.z; }
+          if (argbOut) argbOut[q] = packArgb(c.x, c.y, c.z);
+          if (sigOut) sigOut[q] = sig;
+        }
+    }
+  }
+
+  // event counters: one striped atomic pair per warp
+  const uint32_t wb = __reduce_add_sync(0xffffffffu, nBounces);
+  const uint32_t ws = __reduce_add_sync(0xffffffffu, nShadow);
+  if ((threadIdx.x & 31) == 0 && counters)
+  {
+    const uint32_t slot = (blockIdx.x * (TRACE_THREADS / 32) + (threadIdx.x >> 5)) & 31u;
+    atomicAdd(&counters[slot * 2], (unsigned long long)wb);
+    atomicAdd(&counters[slot * 2 + 1], (unsigned long long)ws);
+  }
+}
+
+int launchTrace(const TraceWork & w, cudaStream_t st)
+{
+  const FrameParams & fp = w.fp;
+  uint64_t nThreads;
+  if (fp.sampleNum > 0)
+    nThreads = fp.p1 - fp.p0;
+  else
+  {
+    // block origins in [p0, p1): the host computed firstRank; count = originsBefore(p1) - firstRank is passed via p1 bound
+    const uint32_t a = (uint32_t)(-fp.sampleNum);
+    const uint32_t bw = (fp.W + a - 1) / a, bh = (fp.H + a - 1) / a;
+    nThreads = (uint64_t)bw * bh - fp.firstRank;   // upper bound; threads past p1 exit
+  }
+  if (nThreads == 0) return 0;
+  const uint32_t smem = (w.sceneBytes + 15u) & ~15u;
+  static uint32_t smemOptedIn = 0;
+  if (smem > 48 * 1024 && smem > smemOptedIn)
+  {
+    cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smemOptedIn = smem;
+  }
+  const uint32_t blocks = (uint32_t)((nThreads + TRACE_THREADS - 1) / TRACE_THREADS);
+  k_trace<<<blocks, TRACE_THREADS, smem, st>>>(reinterpret_cast<const unsigned char *>(w.sceneBlob), smem, fp, w.sampleStates,
+                                               w.image, w.argbOut, w.sigOut, w.counters);
+  return 1;
+}
+
+// =====================================================================================================================
+// K3: imagePixel() + argb() for the whole image (reference Render.cpp:103-114, Color.cpp:114-117)
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) k_resolve(const float * __restrict__ image, unsigned long long nPixels, int additiveCounter,
+                                                 float * __restrict__ rgbfOut, uint32_t * __restrict__ argbOut)
+{
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const float div = float(additiveCounter);
+  for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < nPixels; p += stride)
+  {
+    float r = image[p * 3], g = image[p * 3 + 1], b = image[p * 3 + 2];
+    if (additiveCounter > 1 && fabsf(div) > RFX_VSN) { r = r / div; g = g / div; b = b / div; }
+    if (rgbfOut) { rgbfOut[p * 3] = r; rgbfOut[p * 3 + 1] = g; rgbfOut[p * 3 + 2] = b; }
+    if (argbOut) argbOut[p] = packArgb(r, g, b);
+  }
+}
+
+int launchResolve(const float * image, uint64_t nPixels, int additiveCounter, float * rgbfOut, uint32_t * argbOut, cudaStream_t st)
+{
+  if (!nPixels) return 0;
+  const uint32_t blocks = (uint32_t)((nPixels + 255) / 256 < 148ull * 16 ? (nPixels + 255) / 256 : 148ull * 16);
+  k_resolve<<<blocks, 256, 0, st>>>(image, (unsigned long long)nPixels, additiveCounter, rgbfOut, argbOut);
+  return 1;
+}
+
+__global__ void __launch_bounds__(256) k_clear(float * __restrict__ p, unsigned long long n)
+{
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = 0.0f;
+}
+
+int launchClear(float * image, uint64_t nFloats, cudaStream_t st)
+{
+  if (!nFloats) return 0;
+  const uint32_t blocks = (uint32_t)((nFloats + 255) / 256 < 148ull * 16 ? (nFloats + 255) / 256 : 148ull * 16);
+  k_clear<<<blocks, 256, 0, st>>>(image, (unsigned long long)nFloats);
+  return 1;
+}
+
+} // namespace rfx

@@ -1,0 +1,84 @@
+// rfx_types.h — POD records shared by the host flattening code (rfx_capi.cu) and the sm_100a kernels (rfx_kernels.cu).
+//
+// HBM layout of a scene ("scene blob", one contiguous allocation, copied into shared memory by every CTA):
+//   SceneHeader | Light[nLights] | float4 sphere[nSpheres] (cx,cy,cz,r^2) | Triangle[nTris] | Plane[nPlanes] |
+//   Material[nObjects] (sorted order: spheres, triangles, planes) | TexRef[nTextures]
+// Objects are grouped by kind so the intersection loops are branch-free over a homogeneous array; every record keeps
+// the object's insertion index so closest-hit ties resolve exactly as the reference's list walk does
+// (first inserted wins, reference Scene.cpp:98) and the shadow loop can skip the hit object (Scene.cpp:135).
+#pragma once
+#include <stdint.h>
+
+namespace rfx
+{
+
+struct Material          // reference Material.h:8-12 (+ where the colour comes from)
+{
+  float r, g, b;
+  float reflectivity;
+  int type;              // 0 metal, 1 dielectric
+  int order;             // insertion index in the reference's sceneObjects list
+  int tex;               // triangles: texture id or -1
+  int pad;
+};
+
+struct Light             // reference OmniLight.h:8-11
+{
+  float ox, oy, oz, radius;
+  float r, g, b, power;
+};
+
+struct Triangle          // reference Triangle.h:10-16 (what trace() reads)
+{
+  float v0[3];
+  float ax[9];           // axTrans = inverse[ v2-v0 | v1-v0 | -n ], row-major
+  float n[3];
+  float tuv[4];          // tuvTrans rows 1-2, columns 1-2 (column 3 and row 3 only ever meet zeros)
+  float tu0, tv0;
+};
+
+struct Plane             // reference Plane.h
+{
+  float pos[3];
+  float n[3];
+};
+
+struct TexRef
+{
+  const uint32_t * px;   // device pointer, 0xAARRGGBB, row 0 = v 0; NULL = empty texture (checker fallback)
+  uint32_t w, h;
+};
+
+struct SceneHeader
+{
+  int nSpheres, nTris, nPlanes, nLights, nTextures;
+  int skyTex;                       // texture id or -1
+  float ambient[3], ambientPower;   // Scene::diffLightColor / diffLightPower
+  float env[3];                     // Scene::envColor
+  float halfTileW, halfTileH;       // Skybox::halfTileWidth/Height
+  uint32_t offLights, offSpheres, offTris, offPlanes, offMats, offTex;   // byte offsets inside the blob
+  uint32_t bytes;                   // blob size
+  const float * byteLut;            // 256 floats: float(i) / 255.0f computed on the host (reference Color.cpp:11-13)
+};
+
+struct FrameParams                  // one renderBegin snapshot + the renderNext slice being rendered
+{
+  float eye[3];
+  float view[9];                    // row-major _11.._33
+  float rz, wHalf, hHalf;           // Render.cpp:148-150 (rz from host tanf)
+  uint32_t W, H;
+  int reflNum;                      // renderReflectNum
+  int sampleNum;                    // renderSampleNum (> 0 grid SSAA, < 0 block preview)
+  int jitter;                       // renderAdditive: draw rndx, rndy per pixel from the Render.cpp TU stream
+  int accumulate;                   // additiveCounter > 1: image += colour
+  uint32_t seedRender;              // Render.cpp TU LCG state at the first pixel of this slice
+  uint64_t p0, p1;                  // linear pixel range [p0, p1) of this slice, scan order (y-major)
+  uint64_t firstRank;               // block-preview mode: number of block origins before p0
+};
+
+struct Counters                     // device-side event counters (uint64 each)
+{
+  unsigned long long rays, bounces, shadowRays, samples;
+};
+
+} // namespace rfx

@@ -1,0 +1,70 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/ref_render, built from /root/reference by
+oracle/Makefile).  Run in the build container only:  python tests/golden/make_golden.py
+
+Each vector stores the inputs needed to replay it (scene name, camera floats, size, depth, samples, seed) and the
+reference's outputs (ARGB, and the float image for the small cases), zlib-compressed by numpy.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as O            # noqa: E402
+from reflaxman_b200 import scenes as S      # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def textured_default():
+    sky = S.synthetic_texture(512, 384, 7)
+    floor = S.synthetic_texture(256, 256, 11)
+    return S.default_scene(skybox=sky, floor=floor)
+
+
+def small_synth():
+    return S.synthetic_scene(n_side=6, floor=S.synthetic_texture(128, 128, 3))
+
+
+CASES = [
+    # name, scene factory (None = the reference's own built-in scene), W, H, refl, samples, additive passes, frames, seed, keep float
+    ("default_160x120_d20", None, 160, 120, 20, 1, 0, 1, 12345, True),
+    ("default_160x120_d4_seed777", None, 160, 120, 4, 1, 0, 1, 777, True),
+    ("default_96x64_ss3", None, 96, 64, 15, 3, 0, 1, 12345, True),
+    ("default_96x64_block4", None, 96, 64, 4, -4, 0, 1, 12345, True),
+    ("default_96x64_additive3", None, 96, 64, 15, 1, 3, 1, 12345, True),
+    ("default_64x48_2frames", None, 64, 48, 20, 1, 0, 2, 12345, True),
+    ("textured_160x120_d20", textured_default, 160, 120, 20, 1, 0, 1, 12345, True),
+    ("synth36_128x72_d8", small_synth, 128, 72, 8, 1, 0, 1, 12345, True),
+]
+
+
+def main():
+    O.build(ref=True)
+    assert O.have_ref(), "oracle/_ref/ref_render missing: /root/reference not available?"
+    index = {}
+    for name, factory, W, H, refl, samples, add, frames, seed, keepf in CASES:
+        scene = factory() if factory else None
+        info, imgs = O.run_reference(W, H, refl=refl, samples=samples, additive_passes=add, frames=frames, scene=scene, seed=seed)
+        data = {"W": W, "H": H, "refl": refl, "samples": samples, "additive": add, "frames": frames, "seed": seed}
+        for i, (rgbf, argb) in enumerate(imgs):
+            data["argb%d" % i] = argb
+            if keepf:
+                data["rgbf%d" % i] = rgbf
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **data)
+        index[name] = hashlib.sha256(imgs[-1][1].tobytes()).hexdigest()
+        print(name, index[name][:16])
+    # full-size hashes only (images are too big to commit): config 1 and config 2
+    with open(os.path.join(OUT, "full_size_sha256.txt"), "w") as f:
+        for W, H in ((1024, 768), (1920, 1080)):
+            info, imgs = O.run_reference(W, H, refl=20, seed=12345)
+            hs = hashlib.sha256(imgs[0][1].tobytes()).hexdigest()
+            hf = hashlib.sha256(imgs[0][0].tobytes()).hexdigest()
+            f.write("default_%dx%d_d20_seed12345 argb %s rgbf %s\n" % (W, H, hs, hf))
+            print(W, H, hs[:16])
+
+
+if __name__ == "__main__":
+    main()

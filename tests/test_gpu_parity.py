@@ -1,0 +1,134 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against
+  (1) the golden vectors generated from the unmodified reference (committed fixtures),
+  (2) the CPU oracle on the same seeded inputs at sizes it finishes in seconds,
+  (3) the unmodified reference binary when oracle/_ref travelled to the box.
+Bar (BASELINE.json): <= 1 LSB/channel on >= 99.9 % of pixels, none > 4 LSB.  The only arithmetic that may differ is
+powf (CUDA vs glibc); everything else is expected to be identical, so we also require identical hit-path signatures
+and report the exact-match fraction."""
+import numpy as np
+import pytest
+
+import cases
+from reflaxman_b200 import scenes as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi(rfx_lib):
+    from reflaxman_b200 import capi
+    return capi
+
+
+@pytest.mark.parametrize("name", cases.GOLDEN)
+def test_gpu_matches_golden(capi, name):
+    g = cases.load_golden(name)
+    eng = cases.GpuEngine(capi, g["scene"], g["W"], g["H"], g["seed"])
+    try:
+        frames = cases.replay(eng, g)
+        for i, (rgbf, argb) in enumerate(frames):
+            st = cases.assert_parity(argb, g["argb%d" % i], "%s frame %d" % (name, i))
+            # float image: identical up to powf rounding (<= a few ulp of a colour contribution)
+            assert np.max(np.abs(rgbf - g["rgbf%d" % i])) < 2e-5, name
+            assert st["frac_exact"] > 0.995, (name, st)
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("chunk", [1, 777, 4096])
+def test_render_next_slicing_is_invisible(capi, chunk):
+    """renderNext(pixels) in arbitrary slices == one full-frame call (reference Render.cpp:198-211 cursor)."""
+    scene = S.default_scene()
+    cam = S.default_camera()
+    a = cases.GpuEngine(capi, scene, 80, 60, 99)
+    b = cases.GpuEngine(capi, scene, 80, 60, 99, chunk=chunk)
+    try:
+        for samples in (1, 2, -3):
+            a.render(cam, 8, samples, False)
+            b.render(cam, 8, samples, False)
+            assert np.array_equal(a.read()[0].view(np.uint32), b.read()[0].view(np.uint32)), samples
+        assert a.c.get_seeds() == b.c.get_seeds()
+    finally:
+        a.close(); b.close()
+
+
+def test_signatures_and_rays_match_oracle_config1(capi, oracle):
+    """config 1 (1024x768, depth 20): identical hit paths on 100 % of pixels, identical ray count, parity bar met."""
+    W, H = 1024, 768
+    cam = S.default_camera()
+    o = oracle.OracleRender(S.default_scene(), W, H, seed=12345).render(cam, 20, want_sig=True)
+    _, oargb = o.resolve()
+    c = capi.Context(0)
+    try:
+        c.load_scene(S.default_scene()); c.set_seeds(12345, 12345); c.set_image_size(W, H)
+        c.enable_signatures(True)
+        c.stats_reset()
+        c.render(cam, 20)
+        argb = c.read_argb()
+        sig = c.read_signatures()
+        st = c.stats()
+        assert np.array_equal(sig, o.sig), "hit-path signatures differ on %d pixels" % int((sig != o.sig).sum())
+        assert st["rays"] == o.counters["rays"] and st["bounces"] == o.counters["bounces"]
+        cases.assert_parity(argb, oargb, "config 1")
+        assert c.get_seeds()[0] == int(o.seeds[0])
+    finally:
+        c.close()
+
+
+def test_gpu_vs_reference_binary_config2(capi, oracle):
+    """config 2 (1920x1080, depth 20, seed 12345) against the unmodified reference itself."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/ref_render did not travel to this box")
+    W, H = 1920, 1080
+    info, imgs = oracle.run_reference(W, H, refl=20, seed=12345)
+    c = capi.Context(0)
+    try:
+        c.load_scene(S.default_scene()); c.set_seeds(12345, 12345); c.set_image_size(W, H)
+        c.render(S.default_camera(), 20)
+        st = cases.assert_parity(c.read_argb(), imgs[0][1], "config 2 vs reference")
+        print("config 2 parity:", st)
+    finally:
+        c.close()
+
+
+def test_batch_frames_continue_the_stream(capi, oracle):
+    """rfx_render_frames over a camera path == the oracle rendering the same frames in one process (stream
+    continues from frame to frame); and a context that skips ahead reproduces a later frame (frame sharding)."""
+    W, H, refl = 96, 54, 20
+    cams = S.orbit_cameras(12)[:5]
+    o = oracle.OracleRender(S.default_scene(), W, H, seed=2024)
+    want = [o.render(cam, refl).resolve()[1] for cam in cams]
+    c = capi.Context(0)
+    d = capi.Context(0)
+    try:
+        for ctx in (c, d):
+            ctx.load_scene(S.default_scene()); ctx.set_seeds(2024, 2024); ctx.set_image_size(W, H)
+        got = c.render_frames(cams, refl)
+        for i in range(len(cams)):
+            cases.assert_parity(got[i], want[i], "batch frame %d" % i)
+        d.skip_samples(3 * W * H)
+        late = d.render_frames(cams[3:], refl)
+        assert np.array_equal(late[0], got[3]) and np.array_equal(late[1], got[4])
+    finally:
+        c.close(); d.close()
+
+
+def test_error_behaviour(capi):
+    c = capi.Context(0)
+    try:
+        with pytest.raises(capi.RfxError):
+            c.render_begin(20)                 # no image size yet
+        c.set_image_size(8, 8)
+        with pytest.raises(capi.RfxError):
+            c.render_begin(0)                  # reflectNum must be > 0 (reference asserts, Render.cpp:118)
+        with pytest.raises(capi.RfxError):
+            c.render_begin(5, 0)               # sampleNum != 0 (Render.cpp:119)
+        assert c.render_next(10) is False      # not in progress -> false (Render.cpp:143-144)
+        c.load_scene(S.default_scene())
+        c.set_camera(S.default_camera())
+        c.render_begin(3)
+        assert c.render_next(10) is True and abs(c.progress() - 100.0 * 10 / 64) < 1e-4
+        assert c.render_next(1000) is False and c.progress() == 100.0 and not c.in_progress()
+        assert np.array_equal(c.read_pixel(-1, 0), np.zeros(3, np.float32))   # Render.cpp:112-113
+    finally:
+        c.close()

@@ -1,0 +1,92 @@
+"""CPU tests: pin the oracle (our C restatement) against the golden vectors generated from the unmodified
+reference, and — where the reference binary is present — against the reference itself at config-1 size."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from reflaxman_b200 import scenes as S
+
+
+@pytest.mark.parametrize("name", cases.GOLDEN)
+def test_oracle_matches_golden_bit_exact(oracle, name):
+    g = cases.load_golden(name)
+    eng = cases.OracleEngine(oracle, g["scene"], g["W"], g["H"], g["seed"])
+    frames = cases.replay(eng, g)
+    for i, (rgbf, argb) in enumerate(frames):
+        assert np.array_equal(argb, g["argb%d" % i]), "%s frame %d: ARGB differs from the reference" % (name, i)
+        assert np.array_equal(rgbf.view(np.uint32), g["rgbf%d" % i].view(np.uint32)), "%s frame %d: float image differs" % (name, i)
+
+
+def test_oracle_thread_count_invariance(oracle):
+    cam = S.default_camera()
+    a = oracle.OracleRender(S.default_scene(), 96, 64, nthreads=1).render(cam, 20).resolve()[1]
+    b = oracle.OracleRender(S.default_scene(), 96, 64, nthreads=7).render(cam, 20).resolve()[1]
+    assert np.array_equal(a, b)
+
+
+def test_oracle_config1_hash(oracle):
+    """config 1 (1024x768, depth 20, seed 12345): the port's images hash to what the reference produced."""
+    want = {}
+    with open(os.path.join(cases.GOLDEN_DIR, "full_size_sha256.txt")) as f:
+        for line in f:
+            p = line.split()
+            want[p[0]] = (p[2], p[4])
+    r = oracle.OracleRender(S.default_scene(), 1024, 768, seed=12345).render(S.default_camera(), 20)
+    rgbf, argb = r.resolve()
+    assert hashlib.sha256(argb.tobytes()).hexdigest() == want["default_1024x768_d20_seed12345"][0]
+    assert hashlib.sha256(rgbf.tobytes()).hexdigest() == want["default_1024x768_d20_seed12345"][1]
+    # 3.2111 rays per pixel at config 1
+    assert abs(r.counters["rays"] / (1024 * 768) - 3.2111) < 1e-3
+
+
+def test_oracle_vs_reference_binary(oracle):
+    """Where oracle/_ref/ref_render exists (build container and, via the gpurun snapshot, the GPU box): a scene and a
+    camera the golden set does not contain, chunked renderNext, bit-exact."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/ref_render not built here")
+    scene = cases.small_synth()
+    cams = S.orbit_cameras(8)[3:5]
+    info, imgs = oracle.run_reference(120, 80, refl=6, frames=2, cams=cams, scene=scene, seed=4242, chunk=997)
+    r = oracle.OracleRender(scene, 120, 80, seed=4242)
+    for i, cam in enumerate(cams):
+        rgbf, argb = r.render(cam, 6).resolve()
+        assert np.array_equal(argb, imgs[i][1])
+        assert np.array_equal(rgbf.view(np.uint32), imgs[i][0].view(np.uint32))
+
+
+def test_camera_lookat_matches_reference_ctor(oracle):
+    """scenes.camera_lookat (numpy float32) == the oracle's restatement of Camera(eye, at, fov), bit for bit."""
+    import math
+    for k in range(16):
+        a = 2.0 * math.pi * k / 16
+        c, s = math.cos(a), math.sin(a)
+        rot = lambda p: (np.float32(c * p[0] + s * p[2]), np.float32(p[1]), np.float32(-s * p[0] + c * p[2]))
+        eye, at = (S.DEFAULT_EYE, S.DEFAULT_AT) if k == 0 else (rot(S.DEFAULT_EYE), rot(S.DEFAULT_AT))
+        v_np = S.camera_lookat(eye, at)[1]
+        v_c = oracle.camera_lookat(eye, at)
+        assert np.array_equal(v_np.view(np.uint32), v_c.view(np.uint32)), k
+
+
+def test_rand_dirs_parallel_model(oracle):
+    """The parallel formulation K1 implements (jump-ahead + accept flag + rank) reproduces the serial stream."""
+    seed, n = 12345, 5000
+    dirs, end_state = oracle.rand_dirs(seed, n)
+    A, C = 214013, 2531011
+    m = 3 * (2 * n + 4096)
+    st = np.empty(m + 1, np.uint32)
+    s = seed
+    st[0] = s
+    for i in range(m):
+        s = (A * s + C) & 0xFFFFFFFF
+        st[i + 1] = s
+    r = ((st[1:] >> 16) & 0x7FFF).astype(np.float32)
+    v = (r / np.float32(16383.5) - np.float32(1.0)).reshape(-1, 3)
+    sq = (v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]) + v[:, 2] * v[:, 2]
+    acc = np.nonzero(~(sq > np.float32(1.0)))[0]
+    assert len(acc) >= n
+    assert np.array_equal(v[acc[:n]].view(np.uint32), dirs.view(np.uint32))
+    assert int(st[3 * (acc[n - 1] + 1)]) == end_state
+    assert abs(len(acc) / (m // 3) - 0.5236) < 0.01
