@@ -201,7 +201,8 @@ def run_ours(args):
 
     out_dev = torch.empty((F, H, W), dtype=torch.int32, device="cuda")      # F * 8.3 MB: larger than the 126 MB L2 for F >= 16
     out_host = torch.empty((F, H, W), dtype=torch.int32).pin_memory()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()            # explicit stream: our kernels and the timing events share it
+    torch.cuda.set_stream(stream)
 
     def barrier():
         if world > 1:

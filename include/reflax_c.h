@@ -129,7 +129,10 @@ RFX_API int rfx_synchronize(rfx_ctx * ctx);
 /* ---- bookkeeping --------------------------------------------------------------------------------------- */
 RFX_API int rfx_get_stats(rfx_ctx * ctx, rfx_stats * out);     /* synchronises */
 RFX_API int rfx_stats_reset(rfx_ctx * ctx);
-RFX_API int rfx_enable_profiling(rfx_ctx * ctx, int on);       /* bracket every K2 launch with CUDA events (bench roofline) */
+RFX_API int rfx_enable_profiling(rfx_ctx * ctx, int on);
+/* kernel selection: 0 = automatic (constant-bank kernel when the scene fits, shared-memory kernel otherwise),
+ * 1 = constant-bank kernel if it fits, 2 = always the shared-memory kernel.  Results are identical; tests use it. */
+RFX_API int rfx_force_path(rfx_ctx * ctx, int path);       /* bracket every K2 launch with CUDA events (bench roofline) */
 
 #ifdef __cplusplus
 }

@@ -10,8 +10,8 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("rfx_kernels.cu", "rfx_capi.cu")]
-HDR = [os.path.join(HERE, "csrc", f) for f in ("rfx_kernels.h", "rfx_types.h")] + [os.path.join(HERE, "..", "include", "reflax_c.h")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("rfx_kernels.cu", "rfx_trace_small.cu", "rfx_capi.cu")]
+HDR = [os.path.join(HERE, "csrc", f) for f in ("rfx_kernels.h", "rfx_types.h", "rfx_device.cuh")] + [os.path.join(HERE, "..", "include", "reflax_c.h")]
 OUT = os.path.join(HERE, "libreflax_b200.so")
 
 NVCC_FLAGS = [
@@ -29,16 +29,17 @@ def stale():
     return any(os.path.getmtime(p) > t for p in SRC + HDR + [os.path.abspath(__file__)])
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an experimental variant (tools/variants.py) next to the product library"""
+    if out is None and not force and not stale():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", OUT, *SRC]
+    cmd = [nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-o", out or OUT, *SRC]
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
-    return OUT
+    return out or OUT
 
 
 if __name__ == "__main__":

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libreflax_b200.so")
+LIB_PATH = os.environ.get("RFX_LIB") or os.path.join(HERE, "libreflax_b200.so")   # RFX_LIB: experimental variant (tools/variants.py)
 
 _fp = C.POINTER(C.c_float)
 _u32p = C.POINTER(C.c_uint32)
@@ -67,6 +67,7 @@ SYMBOLS = [
     ("rfx_get_stats", C.c_int, [C.c_void_p, C.POINTER(RfxStats)]),
     ("rfx_stats_reset", C.c_int, [C.c_void_p]),
     ("rfx_enable_profiling", C.c_int, [C.c_void_p, C.c_int]),
+    ("rfx_force_path", C.c_int, [C.c_void_p, C.c_int]),
 ]
 
 _lib = None
@@ -265,6 +266,9 @@ class Context:
 
     def enable_profiling(self, on=True):
         self._ck(self.L.rfx_enable_profiling(self.h, 1 if on else 0), "rfx_enable_profiling")
+
+    def force_path(self, path):
+        self._ck(self.L.rfx_force_path(self.h, path), "rfx_force_path")
 
     def device_info(self):
         d = RfxDeviceInfo()

@@ -85,6 +85,8 @@ struct rfx_ctx
 
   // ---- device scene
   unsigned char * dBlob = nullptr; size_t blobCap = 0; uint32_t blobBytes = 0;
+  SmallScene small; bool smallOk = false;   // constant-bank form of the same scene, when it fits
+  int forcePath = 0;                        // 0 auto, 1 small (constant bank), 2 big (shared memory) — tests exercise both
   float * dLut = nullptr;
 
   // ---- camera + render state (reference Render.h:9-27)
@@ -251,6 +253,30 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
   CK(cudaStreamSynchronize(st));
   ctx->stats.h2d_bytes += off;
   ctx->blobBytes = (uint32_t)off;
+
+  // constant-bank form (rfx_trace_small.cu)
+  ctx->smallOk = sph.size() <= (size_t)SMALL_MAX_SPHERES && tri.size() <= (size_t)SMALL_MAX_TRIS && pla.size() <= (size_t)SMALL_MAX_PLANES &&
+                 ctx->lights.size() <= (size_t)SMALL_MAX_LIGHTS && ctx->tex.size() <= (size_t)SMALL_MAX_TEX;
+  if (ctx->smallOk)
+  {
+    SmallScene & ss = ctx->small;
+    memset(&ss, 0, sizeof(ss));
+    ss.nS = h.nSpheres; ss.nT = h.nTris; ss.nP = h.nPlanes; ss.nL = h.nLights;
+    ss.skyTex = h.skyTex; ss.halfTileW = h.halfTileW; ss.halfTileH = h.halfTileH;
+    ss.ambientPower = h.ambientPower;
+    memcpy(ss.ambient, h.ambient, sizeof(ss.ambient));
+    memcpy(ss.env, h.env, sizeof(ss.env));
+    ss.byteLut = ctx->dLut;
+    for (size_t i = 0; i < sph.size(); i++)
+    {
+      ss.sph[i] = make_float4(sph[i]->center[0], sph[i]->center[1], sph[i]->center[2], sph[i]->sqRadius);
+      ss.mat[i] = sph[i]->mat;
+    }
+    for (size_t i = 0; i < tri.size(); i++) { ss.tri[i] = tri[i]->tri; ss.mat[SMALL_MAX_SPHERES + i] = tri[i]->mat; }
+    for (size_t i = 0; i < pla.size(); i++) { ss.pl[i] = pla[i]->plane; ss.mat[SMALL_MAX_SPHERES + SMALL_MAX_TRIS + i] = pla[i]->mat; }
+    for (size_t i = 0; i < ctx->lights.size(); i++) ss.light[i] = ctx->lights[i];
+    for (size_t i = 0; i < ctx->tex.size(); i++) { ss.tex[i].px = ctx->tex[i].dev; ss.tex[i].w = ctx->tex[i].w; ss.tex[i].h = ctx->tex[i].h; }
+  }
   ctx->sceneDirty = false;
   return RFX_OK;
 }
@@ -337,7 +363,8 @@ int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, boo
         evA = ctx->evPool[ctx->evUsed++]; evB = ctx->evPool[ctx->evUsed++];
         CK(cudaEventRecord(evA, st));
       }
-      ctx->stats.kernel_launches += launchTrace(w, st);
+      const bool useSmall = ctx->forcePath == 1 ? ctx->smallOk : ctx->forcePath == 2 ? false : ctx->smallOk;
+      ctx->stats.kernel_launches += useSmall ? launchTraceSmall(ctx->small, w, st) : launchTrace(w, st);
       if (evB) CK(cudaEventRecord(evB, st));
       CK(cudaGetLastError());
       ctx->stats.samples += nCalls;
@@ -898,6 +925,13 @@ int rfx_stats_reset(rfx_ctx * ctx)
   CK(cudaMemset(ctx->dCounters, 0, 64 * sizeof(unsigned long long)));
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   ctx->evUsed = 0;
+  return RFX_OK;
+}
+
+int rfx_force_path(rfx_ctx * ctx, int path)
+{
+  if (!ctx || path < 0 || path > 2) return RFX_ERR_ARG;
+  ctx->forcePath = path;
   return RFX_OK;
 }
 

@@ -23,49 +23,14 @@
 //   k_trace pixel loop          Render.cpp:136-215
 //   k_resolve                   Render.cpp:103-114, Color.cpp:114-117
 #include "rfx_kernels.h"
+#include "rfx_device.cuh"
 #include <float.h>
 #include <math.h>
 
 namespace rfx
 {
 
-#define RFX_VSN 1.08420217248550443e-19f   // sqrtf(FLT_MIN) = 2^-63, reference trace_math.h:17
-#define RFX_DELTA 0.0001f                  // reference trace_math.h:18
-
-// =====================================================================================================================
-// LCG (reference trace_math.h:36-39): g = 214013*g + 2531011 (mod 2^32), draw = (g >> 16) & 0x7FFF
-// =====================================================================================================================
-__host__ __device__ __forceinline__ uint32_t lcgJump(uint32_t s, uint32_t n)
-{
-  // f^n for the affine map f(s) = A s + C by binary powering; the period divides 2^32 so n mod 2^32 is exact
-  uint32_t A = 214013u, C = 2531011u;
-  while (n)
-  {
-    if (n & 1u) s = A * s + C;
-    C = C * (A + 1u);
-    A = A * A;
-    n >>= 1;
-  }
-  return s;
-}
-
 uint32_t lcgJumpHost(uint32_t s, uint64_t n) { return lcgJump(s, (uint32_t)n); }
-
-__device__ __forceinline__ float lcgDrawUnit(uint32_t & s)
-{
-  s = 214013u * s + 2531011u;
-  const int r = (int)((s >> 16) & 0x7FFFu);
-  return float(r) / 16383.5f - 1.f;   // float(fastrand()) / (float(FAST_RAND_MAX) / 2) - 1.f, Vector3.cpp:182-184
-}
-
-// one draw-triple: advances s by three draws; true when the candidate lies inside the unit sphere (Vector3.cpp:185)
-__device__ __forceinline__ bool rngTriple(uint32_t & s, float & x, float & y, float & z)
-{
-  x = lcgDrawUnit(s);
-  y = lcgDrawUnit(s);
-  z = lcgDrawUnit(s);
-  return !((x * x + y * y) + z * z > 1.f);
-}
 
 __global__ void __launch_bounds__(RNG_THREADS) k_rng_count(const uint32_t * __restrict__ stateIn, uint32_t * __restrict__ blockCounts)
 {
@@ -190,35 +155,6 @@ int launchRngRank(const RngWork & w, cudaStream_t st)
 }
 
 // =====================================================================================================================
-// vector helpers (float3 by value; un-contracted, reference evaluation order)
-// =====================================================================================================================
-struct V3 { float x, y, z; };
-__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }
-__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ V3 vscale(V3 a, float f) { return mk(a.x * f, a.y * f, a.z * f); }
-__device__ __forceinline__ float vdot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }       // Vector3.cpp:124-127
-__device__ __forceinline__ float vsqlen(V3 a) { return (a.x * a.x + a.y * a.y) + a.z * a.z; }           // Vector3.cpp:41-44
-__device__ __forceinline__ float vlen(V3 a) { return sqrtf(vsqlen(a)); }                                // Vector3.cpp:36-39
-__device__ __forceinline__ V3 normalizeVec(V3 a)   // Vector3.cpp:55-64 == trace_math.cpp:3-12: three true divides, guarded
-{
-  const float l = vlen(a);
-  if (l > RFX_VSN) return mk(a.x / l, a.y / l, a.z / l);
-  return a;
-}
-__device__ __forceinline__ V3 reflectVec(V3 v, V3 n)   // trace_math.cpp:14-23: v - (2*n) * ((v.n)/(n.n))
-{
-  const float dn = vdot(n, n);
-  if (dn > RFX_VSN)
-  {
-    const float s = vdot(v, n) / dn;
-    return mk(v.x - (n.x * 2.0f) * s, v.y - (n.y * 2.0f) * s, v.z - (n.z * 2.0f) * s);
-  }
-  return v;
-}
-__device__ __forceinline__ float clamp01(float v) { return v < 0.0f ? 0.0f : v > 1.0f ? 1.0f : v; }   // trace_math.h:24
-
-// =====================================================================================================================
 // scene view over the shared-memory copy of the blob
 // =====================================================================================================================
 struct SceneView
@@ -246,68 +182,16 @@ __device__ __forceinline__ SceneView makeView(const unsigned char * base)
 }
 
 // =====================================================================================================================
-// textures (reference Texture.cpp:216-269) and skybox (Skybox.cpp:39-106)
+// textures / skybox: thin adapters from the shared-memory scene view onto the shared samplers (rfx_device.cuh)
 // =====================================================================================================================
-__device__ __forceinline__ V3 texel(const TexRef & t, const float * __restrict__ lut, uint32_t x, uint32_t y)
+__device__ __forceinline__ V3 texSample(const SceneView & sc, int texId, float u, float v)
 {
-  const uint32_t c = __ldg(t.px + (x + t.w * y));
-  // Color(ARGB): float(byte) / 255.0f (Color.cpp:11-13) through the host-computed 256-entry table
-  return mk(__ldg(lut + ((c >> 16) & 0xFFu)), __ldg(lut + ((c >> 8) & 0xFFu)), __ldg(lut + (c & 0xFFu)));
+  return texSampleRef(texId >= 0 ? &sc.tex[texId] : nullptr, sc.h->byteLut, u, v);
 }
-
-__device__ V3 texSample(const SceneView & sc, int texId, float u, float v)
+__device__ __forceinline__ V3 skySample(const SceneView & sc, V3 ray)
 {
-  if (u < 0.0f || u > 1.0f || v < 0.0f || v > 1.0f) return mk(0.0f, 0.0f, 0.0f);
-  const TexRef * t = texId >= 0 ? &sc.tex[texId] : nullptr;
-  if (!t || !t->px)
-  {
-    const float g = ((int(u * 50) % 2) ^ (int(v * 50) % 2)) ? 0.5f : 0.75f;   // Texture.cpp:243
-    return mk(g, g, g);
-  }
-  const float * lut = sc.h->byteLut;
-  const float cu = u < 0.0f ? 0.0f : u > (1.0f - FLT_EPSILON) ? (1.0f - FLT_EPSILON) : u;
-  const float cv = v < 0.0f ? 0.0f : v > (1.0f - FLT_EPSILON) ? (1.0f - FLT_EPSILON) : v;
-  const float fx = cu * float(t->w);
-  const float fy = cv * float(t->h);
-  const uint32_t x = (uint32_t)fx, y = (uint32_t)fy;
-  if (x < t->w - 1 && y < t->h - 1)
-  {
-    const V3 c00 = texel(*t, lut, x, y), c01 = texel(*t, lut, x, y + 1), c10 = texel(*t, lut, x + 1, y), c11 = texel(*t, lut, x + 1, y + 1);
-    const float uf = fx - floorf(fx), vf = fy - floorf(fy);
-    const float uo = 1 - uf, vo = 1 - vf;
-    // (c00*uo + c10*uf)*vo + (c01*uo + c11*uf)*vf, Texture.cpp:264
-    return mk((c00.x * uo + c10.x * uf) * vo + (c01.x * uo + c11.x * uf) * vf,
-              (c00.y * uo + c10.y * uf) * vo + (c01.y * uo + c11.y * uf) * vf,
-              (c00.z * uo + c10.z * uf) * vo + (c01.z * uo + c11.z * uf) * vf);
-  }
-  if (x >= t->w || y >= t->h) return mk(0.0f, 0.0f, 0.0f);   // Texture.cpp:223-224 (unreachable after the clamp)
-  return texel(*t, lut, x, y);
-}
-
-__device__ V3 skySample(const SceneView & sc, V3 ray)
-{
-  const float uLeft = 1.0f / 8.0f, vMid = 3.0f / 6.0f, uFront = 3.0f / 8.0f, uRight = 5.0f / 8.0f, uBack = 7.0f / 8.0f;
-  const float vTop = 5.0f / 6.0f, vBottom = 1.0f / 6.0f;
-  const V3 n = normalizeVec(ray);
-  const float x = n.x, y = n.y, z = n.z;
-  const float ax = fabsf(x) + RFX_VSN, ay = fabsf(y) + RFX_VSN, az = fabsf(z) + RFX_VSN;
-  const float hw = sc.h->halfTileW, hh = sc.h->halfTileH;
   float u, v;
-  if (az >= ax && az >= ay)
-  {
-    if (z > 0) { u = uFront + x / az * hw; v = vMid + y / az * hh; }
-    else       { u = uBack - x / az * hw;  v = vMid + y / az * hh; }
-  }
-  else if (ax >= ay && ax >= az)
-  {
-    if (x > 0) { u = uRight - z / ax * hw; v = vMid + y / ax * hh; }
-    else       { u = uLeft + z / ax * hw;  v = vMid + y / ax * hh; }
-  }
-  else
-  {
-    if (y > 0) { u = uFront + x / ay * hw; v = vTop - z / ay * hh; }      // uTop == uFront == uBottom == 3/8
-    else       { u = uFront + x / ay * hw; v = vBottom + z / ay * hh; }
-  }
+  skyDirToUv(ray, sc.h->halfTileW, sc.h->halfTileH, u, v);
   return texSample(sc, sc.h->skyTex, u, v);
 }
 
@@ -433,8 +317,6 @@ __device__ __forceinline__ bool intersectAll(const SceneView & sc, V3 o, V3 d, i
 // =====================================================================================================================
 // Scene::trace (reference Scene.cpp:73-236)
 // =====================================================================================================================
-#define RFX_SIG(h, ev) ((h) = ((h) ^ (uint32_t)(ev)) * 16777619u)
-
 __device__ V3 traceSample(const SceneView & sc, V3 origin, V3 ray, int reflNumber, V3 randDir,
                           uint32_t & nBounces, uint32_t & nShadow, uint32_t & sig)
 {
@@ -580,15 +462,15 @@ __device__ V3 traceSample(const SceneView & sc, V3 origin, V3 ray, int reflNumbe
 // thread walks its s*s samples in the reference's ssx, ssy order so the sum is formed in the same order), or one
 // thread per block origin in block-preview mode.
 // =====================================================================================================================
-constexpr int TRACE_THREADS = 128;
+#ifndef RFX_BIG_THREADS
+#define RFX_BIG_THREADS 128
+#endif
+#ifndef RFX_BIG_MINBLOCKS
+#define RFX_BIG_MINBLOCKS 1
+#endif
+constexpr int TRACE_THREADS = RFX_BIG_THREADS;
 
-__device__ __forceinline__ uint32_t packArgb(float r, float g, float b)   // Color::argb, Color.cpp:114-117
-{
-  return (((uint32_t)(unsigned char)(r * 255.999f)) << 16) | (((uint32_t)(unsigned char)(g * 255.999f)) << 8) |
-         ((uint32_t)(unsigned char)(b * 255.999f));
-}
-
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(const unsigned char * __restrict__ sceneBlob, uint32_t sceneBytes,
+__global__ void __launch_bounds__(TRACE_THREADS, RFX_BIG_MINBLOCKS) k_trace(const unsigned char * __restrict__ sceneBlob, uint32_t sceneBytes,
                                                          const __grid_constant__ FrameParams fp,
                                                          const uint32_t * __restrict__ sampleStates, float * __restrict__ image,
                                                          uint32_t * __restrict__ argbOut, uint32_t * __restrict__ sigOut,

@@ -44,7 +44,8 @@ struct TraceWork
   uint32_t * sigOut;            // optional per-pixel hit-path signature
   unsigned long long * counters;// device [32][2] striped {bounces, shadowRays}
 };
-int launchTrace(const TraceWork & w, cudaStream_t st);
+int launchTrace(const TraceWork & w, cudaStream_t st);                              // any scene: shared-memory resident blob
+int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st);   // small scenes: constant-bank resident
 
 // ---- K3: resolve (imagePixel + argb) ---------------------------------------------------------------------------
 int launchResolve(const float * image, uint64_t nPixels, int additiveCounter, float * rgbfOut, uint32_t * argbOut, cudaStream_t st);

@@ -8,6 +8,7 @@
 // (first inserted wins, reference Scene.cpp:98) and the shadow loop can skip the hit object (Scene.cpp:135).
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 namespace rfx
 {
@@ -59,6 +60,31 @@ struct SceneHeader
   uint32_t offLights, offSpheres, offTris, offPlanes, offMats, offTex;   // byte offsets inside the blob
   uint32_t bytes;                   // blob size
   const float * byteLut;            // 256 floats: float(i) / 255.0f computed on the host (reference Color.cpp:11-13)
+};
+
+// Small scenes travel as a kernel parameter (constant bank): see rfx_trace_small.cu
+constexpr int SMALL_MAX_SPHERES = 16;
+constexpr int SMALL_MAX_TRIS = 8;
+constexpr int SMALL_MAX_PLANES = 2;
+constexpr int SMALL_MAX_LIGHTS = 4;
+constexpr int SMALL_MAX_TEX = 8;
+constexpr int SMALL_MAX_OBJECTS = SMALL_MAX_SPHERES + SMALL_MAX_TRIS + SMALL_MAX_PLANES;
+
+struct SmallScene
+{
+  int nS, nT, nP, nL;
+  int skyTex;
+  float halfTileW, halfTileH;
+  float ambientPower;
+  float ambient[3];
+  float env[3];
+  const float * byteLut;
+  float4 sph[SMALL_MAX_SPHERES];            // cx, cy, cz, r^2
+  Triangle tri[SMALL_MAX_TRIS];
+  Plane pl[SMALL_MAX_PLANES];
+  Light light[SMALL_MAX_LIGHTS];
+  Material mat[SMALL_MAX_OBJECTS];          // indexed by candidate-mask bit: spheres 0.., triangles 16.., planes 24..
+  TexRef tex[SMALL_MAX_TEX];
 };
 
 struct FrameParams                  // one renderBegin snapshot + the renderNext slice being rendered

@@ -20,10 +20,13 @@ def capi(rfx_lib):
     return capi
 
 
+@pytest.mark.parametrize("path", [1, 2], ids=["constbank", "smem"])
 @pytest.mark.parametrize("name", cases.GOLDEN)
-def test_gpu_matches_golden(capi, name):
+def test_gpu_matches_golden(capi, name, path):
+    """both K2 variants: 1 = constant-bank kernel (small scenes), 2 = shared-memory kernel (any scene)"""
     g = cases.load_golden(name)
     eng = cases.GpuEngine(capi, g["scene"], g["W"], g["H"], g["seed"])
+    eng.c.force_path(path)
     try:
         frames = cases.replay(eng, g)
         for i, (rgbf, argb) in enumerate(frames):
@@ -52,7 +55,8 @@ def test_render_next_slicing_is_invisible(capi, chunk):
         a.close(); b.close()
 
 
-def test_signatures_and_rays_match_oracle_config1(capi, oracle):
+@pytest.mark.parametrize("path", [1, 2], ids=["constbank", "smem"])
+def test_signatures_and_rays_match_oracle_config1(capi, oracle, path):
     """config 1 (1024x768, depth 20): identical hit paths on 100 % of pixels, identical ray count, parity bar met."""
     W, H = 1024, 768
     cam = S.default_camera()
@@ -61,6 +65,7 @@ def test_signatures_and_rays_match_oracle_config1(capi, oracle):
     c = capi.Context(0)
     try:
         c.load_scene(S.default_scene()); c.set_seeds(12345, 12345); c.set_image_size(W, H)
+        c.force_path(path)
         c.enable_signatures(True)
         c.stats_reset()
         c.render(cam, 20)

@@ -1,0 +1,61 @@
+"""Builds kernel variants (compile-time knobs) into build/variants/*.so and, on a GPU box, times K2 for each.
+usage: variants.py build | run"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VDIR = os.path.join(ROOT, "gpurun_variants")
+
+VARIANTS = {
+    # name: (defines, force_path)
+    "small_rolled": (["RFX_SMALL_UNROLL=0"], 1),
+    "small_unrolled": (["RFX_SMALL_UNROLL=1"], 1),
+    "small_rolled_mb6": (["RFX_SMALL_UNROLL=0", "RFX_SMALL_MINBLOCKS=6"], 1),
+    "small_rolled_mb8": (["RFX_SMALL_UNROLL=0", "RFX_SMALL_MINBLOCKS=8"], 1),
+    "small_rolled_t64_mb12": (["RFX_SMALL_UNROLL=0", "RFX_SMALL_THREADS=64", "RFX_SMALL_MINBLOCKS=12"], 1),
+    "small_rolled_t256_mb3": (["RFX_SMALL_UNROLL=0", "RFX_SMALL_THREADS=256", "RFX_SMALL_MINBLOCKS=3"], 1),
+    "big": ([], 2),
+    "big_mb6": (["RFX_BIG_MINBLOCKS=6"], 2),
+    "big_mb8": (["RFX_BIG_MINBLOCKS=8"], 2),
+}
+
+
+def build():
+    from reflaxman_b200 import build as B
+    os.makedirs(VDIR, exist_ok=True)
+    for name, (defs, _) in VARIANTS.items():
+        out = os.path.join(VDIR, name + ".so")
+        B.build(force=True, defines=defs, out=out)
+        print("built", name)
+
+
+def run_one(name):
+    import torch
+    from reflaxman_b200 import capi, scenes as S
+    c = capi.Context(0)
+    c.load_scene(S.default_scene()); c.set_seeds(12345, 12345); c.set_image_size(1920, 1080)
+    c.force_path(VARIANTS[name][1])
+    n = 8
+    out = torch.empty((n, 1080, 1920), dtype=torch.int32, device="cuda")
+    cams = capi.pack_cameras([S.default_camera()] * n)
+    c.render_frames_device(cams, 20, 1, out.data_ptr(), 0); c.synchronize()
+    c.enable_profiling(True); c.stats_reset()
+    c.render_frames_device(cams, 20, 1, out.data_ptr(), 0); c.synchronize()
+    st = c.stats()
+    print(json.dumps({"variant": name, "k2_us": 1e3 * st["trace_kernel_ms"] / st["trace_kernels"], "rays": st["rays"] // n,
+                      "checksum": int(out[0].to(torch.int64).sum().item())}))
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "build":
+        build()
+    elif sys.argv[1] == "run":
+        for name in VARIANTS:
+            so = os.path.join(VDIR, name + ".so")
+            if os.path.exists(so):
+                subprocess.run([sys.executable, __file__, "one", name], env=dict(os.environ, RFX_LIB=so))
+    else:
+        run_one(sys.argv[2])
