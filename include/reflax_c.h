@@ -110,9 +110,29 @@ RFX_API int rfx_additive_counter(const rfx_ctx * ctx);         /* Render::additi
 RFX_API int rfx_in_progress(const rfx_ctx * ctx);              /* Render::inProgress */
 RFX_API int rfx_read_argb(rfx_ctx * ctx, uint32_t * dst);      /* imagePixel(x,y).argb() for the whole image (Pulse.cpp:455-458 / Render::copyImage, Render.cpp:82-101) */
 RFX_API int rfx_read_rgbf(rfx_ctx * ctx, float * dst);         /* imagePixel(x,y) for the whole image, 3 floats per pixel (Render.cpp:103-114) */
+RFX_API int rfx_read_image(rfx_ctx * ctx, float * rgbf, uint32_t * argb, int divide); /* both outputs optional; divide = 0 packs the RAW image as Render::copyImage does (Render.cpp:82-101), 1 = imagePixel semantics */
 RFX_API int rfx_read_pixel(rfx_ctx * ctx, int x, int y, float rgb[3]);            /* Render::imagePixel(x,y) */
 RFX_API int rfx_read_signatures(rfx_ctx * ctx, uint32_t * dst); /* per-pixel hit-path signature of the last pass (parity localiser; enabled by rfx_enable_signatures) */
 RFX_API int rfx_enable_signatures(rfx_ctx * ctx, int on);
+
+/* ---- frame splitting (one frame shared by several GPUs): render only pixels [p0, p1) of the frame latched by
+ * rfx_render_begin.  Ranges must be issued in increasing order; the random streams are advanced over the pixels in between,
+ * so every range consumes exactly the draws it would get in a full-frame render, and rfx_render_finish advances them to the
+ * end of the frame.  argb_device (optional) is a FULL-FRAME ARGB buffer; it may live on another GPU (peer mapping over
+ * NVLink, see rfx_ipc_*): the kernel then stores its pixels straight into the gathering GPU's framebuffer. */
+RFX_API int rfx_render_range(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argb_device, void * stream);
+RFX_API int rfx_render_finish(rfx_ctx * ctx);
+/* device buffers that can be shared between the per-GPU processes of one node (cudaIpc) */
+RFX_API int rfx_buffer_alloc(rfx_ctx * ctx, uint64_t bytes, void ** device_ptr);
+RFX_API int rfx_buffer_free(rfx_ctx * ctx, void * device_ptr);
+RFX_API int rfx_buffer_read(rfx_ctx * ctx, const void * device_ptr, void * host_dst, uint64_t bytes);   /* synchronises */
+RFX_API int rfx_ipc_export(rfx_ctx * ctx, void * device_ptr, unsigned char handle[64]);
+RFX_API int rfx_ipc_import(rfx_ctx * ctx, const unsigned char handle[64], void ** device_ptr);       /* peer mapping of another process's buffer */
+RFX_API int rfx_ipc_close(rfx_ctx * ctx, void * device_ptr);
+
+/* ---- Scene::trace (reference Scene.h:39, Scene.cpp:73-236) for n arbitrary rays: ray i consumes the i-th next randDir of the
+ * stream, exactly as n successive Scene::trace calls would.  origins/rays: 3n floats; rgb out: 3n floats.  Synchronous. */
+RFX_API int rfx_trace_rays(rfx_ctx * ctx, int n, const float * origins, const float * rays, int reflect_num, float * rgb);
 
 /* ---- headless batch path (the bench driver; models Pulse's screenshot flow, Pulse.cpp:174-208, for a camera
  * path).  cams = n_frames x 13 floats (eye[3], view[9], fov).  Each frame is setImageSize-sized, rendered with

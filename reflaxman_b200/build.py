@@ -42,5 +42,23 @@ def build(force=False, verbose=False, defines=(), out=None):
     return out or OUT
 
 
+SHIM_HARNESS = os.path.join(HERE, "..", "build", "shim_harness")
+
+
+def build_shim_harness(force=False):
+    """oracle/ref_harness.cpp — the very source that drives the unmodified reference — compiled against the shim headers
+    (reflaxman_b200/shim) and linked with the CUDA library instead of the reference's src/common: the drop-in proof."""
+    src = os.path.join(HERE, "..", "oracle", "ref_harness.cpp")
+    out = os.path.abspath(SHIM_HARNESS)
+    deps = [src, OUT, os.path.join(HERE, "shim", "rfx_shim.hpp")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.run(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-I" + os.path.join(HERE, "shim"), "-I" + os.path.join(HERE, "..", "include"),
+                    "-o", out, src, "-L" + HERE, "-lreflax_b200", "-Wl,-rpath," + HERE], check=True)
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
+    build_shim_harness(force=True)

@@ -58,7 +58,17 @@ SYMBOLS = [
     ("rfx_in_progress", C.c_int, [C.c_void_p]),
     ("rfx_read_argb", C.c_int, [C.c_void_p, _u32p]),
     ("rfx_read_rgbf", C.c_int, [C.c_void_p, _fp]),
+    ("rfx_read_image", C.c_int, [C.c_void_p, _fp, _u32p, C.c_int]),
     ("rfx_read_pixel", C.c_int, [C.c_void_p, C.c_int, C.c_int, _fp]),
+    ("rfx_trace_rays", C.c_int, [C.c_void_p, C.c_int, _fp, _fp, C.c_int, _fp]),
+    ("rfx_render_range", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    ("rfx_render_finish", C.c_int, [C.c_void_p]),
+    ("rfx_buffer_alloc", C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    ("rfx_buffer_free", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("rfx_buffer_read", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    ("rfx_ipc_export", C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p]),
+    ("rfx_ipc_import", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    ("rfx_ipc_close", C.c_int, [C.c_void_p, C.c_void_p]),
     ("rfx_read_signatures", C.c_int, [C.c_void_p, _u32p]),
     ("rfx_enable_signatures", C.c_int, [C.c_void_p, C.c_int]),
     ("rfx_render_frames", C.c_int, [C.c_void_p, C.c_int, _fp, C.c_int, C.c_int, C.c_void_p]),
@@ -228,6 +238,45 @@ class Context:
         out = (C.c_float * 3)()
         self._ck(self.L.rfx_read_pixel(self.h, x, y, out), "rfx_read_pixel")
         return np.array(out[:], np.float32)
+
+    # ---- frame splitting / shared buffers ---------------------------------------------------------------------
+    def render_range(self, p0, p1, argb_device_ptr=0, stream=0):
+        self._ck(self.L.rfx_render_range(self.h, p0, p1, C.c_void_p(int(argb_device_ptr) or None), C.c_void_p(int(stream) or None)), "rfx_render_range")
+
+    def render_finish(self):
+        self._ck(self.L.rfx_render_finish(self.h), "rfx_render_finish")
+
+    def buffer_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._ck(self.L.rfx_buffer_alloc(self.h, nbytes, C.byref(p)), "rfx_buffer_alloc")
+        return p.value
+
+    def buffer_free(self, ptr):
+        self._ck(self.L.rfx_buffer_free(self.h, C.c_void_p(ptr)), "rfx_buffer_free")
+
+    def buffer_read(self, ptr, out):
+        self._ck(self.L.rfx_buffer_read(self.h, C.c_void_p(ptr), C.c_void_p(out.ctypes.data), out.nbytes), "rfx_buffer_read")
+        return out
+
+    def ipc_export(self, ptr):
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.rfx_ipc_export(self.h, C.c_void_p(ptr), buf), "rfx_ipc_export")
+        return buf.raw
+
+    def ipc_import(self, handle):
+        p = C.c_void_p()
+        self._ck(self.L.rfx_ipc_import(self.h, handle, C.byref(p)), "rfx_ipc_import")
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._ck(self.L.rfx_ipc_close(self.h, C.c_void_p(ptr)), "rfx_ipc_close")
+
+    def trace_rays(self, origins, rays, refl):
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        r = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 3)
+        out = np.empty_like(o)
+        self._ck(self.L.rfx_trace_rays(self.h, o.shape[0], o.ctypes.data_as(_fp), r.ctypes.data_as(_fp), refl, out.ctypes.data_as(_fp)), "rfx_trace_rays")
+        return out
 
     def enable_signatures(self, on=True):
         self._ck(self.L.rfx_enable_signatures(self.h, 1 if on else 0), "rfx_enable_signatures")

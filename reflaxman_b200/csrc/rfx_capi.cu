@@ -105,6 +105,7 @@ struct rfx_ctx
   uint32_t * dBlockCounts = nullptr, * dBlockOffsets = nullptr; size_t blocksCap = 0, offsCap = 0;
   uint32_t * dSampleStates = nullptr; size_t statesCap = 0;
   int * dStatus = nullptr;
+  float * dRays = nullptr; size_t raysCap = 0;   // rfx_trace_rays scratch
 
   // ---- staging for the host batch path
   uint32_t * dFrame[3] = { nullptr, nullptr, nullptr }; size_t frameCap = 0;
@@ -453,7 +454,7 @@ void rfx_destroy(rfx_ctx * ctx)
   for (HostTex & t : ctx->tex) if (t.dev) cudaFree(t.dev);
   cudaFree(ctx->dBlob); cudaFree(ctx->dLut); cudaFree(ctx->dImage); cudaFree(ctx->dSig); cudaFree(ctx->dRng);
   cudaFree(ctx->dBlockCounts); cudaFree(ctx->dBlockOffsets); cudaFree(ctx->dSampleStates); cudaFree(ctx->dStatus);
-  cudaFree(ctx->dCounters);
+  cudaFree(ctx->dCounters); cudaFree(ctx->dRays);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   for (int i = 0; i < 3; i++)
   {
@@ -716,6 +717,119 @@ int rfx_render_next(rfx_ctx * ctx, uint32_t pixels)
   return ctx->inProgress ? 1 : 0;
 }
 
+// number of Scene::trace calls the reference makes for pixels [p0, p1) of the latched frame
+static uint64_t callsIn(const rfx_ctx * ctx, uint64_t p0, uint64_t p1)
+{
+  if (ctx->sampleNum > 0) return (p1 - p0) * (uint64_t)ctx->sampleNum * (uint64_t)ctx->sampleNum;
+  const uint32_t a = (uint32_t)(-ctx->sampleNum);
+  return originsBefore(p1, ctx->W, a) - originsBefore(p0, ctx->W, a);
+}
+
+static int skipPixels(rfx_ctx * ctx, uint64_t p0, uint64_t p1, cudaStream_t st)
+{
+  int rc;
+  uint64_t n = callsIn(ctx, p0, p1);
+  const uint64_t chunk = 1ull << 28;
+  while (n > 0)
+  {
+    const uint64_t m = std::min(n, chunk);
+    if ((rc = rankSamples(ctx, m, true, st)) != RFX_OK) return rc;
+    n -= m;
+  }
+  if (ctx->snap.jitter && ctx->sampleNum > 0) ctx->seedRender = lcgJumpHost(ctx->seedRender, 2 * (p1 - p0));
+  return RFX_OK;
+}
+
+int rfx_render_range(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argb_device, void * stream)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  const uint64_t total = (uint64_t)ctx->W * ctx->H;
+  if (!ctx->inProgress) return fail(ctx, RFX_ERR_ARG, "rfx_render_range: no frame in progress");
+  if (p0 > p1 || p1 > total || p0 < ctx->cursor) return fail(ctx, RFX_ERR_ARG, "rfx_render_range: ranges must be increasing and inside the frame");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  int rc;
+  if ((rc = useStream(ctx, st)) != RFX_OK) return rc;
+  if ((rc = uploadScene(ctx, st)) != RFX_OK) return rc;
+  if (ctx->sigOn && (rc = ensure(ctx, ctx->dSig, ctx->sigCap, (size_t)total)) != RFX_OK) return rc;
+  if (p0 > ctx->cursor && (rc = skipPixels(ctx, ctx->cursor, p0, st)) != RFX_OK) return rc;
+  if ((rc = renderRange(ctx, p0, p1, argb_device, argb_device == nullptr, st)) != RFX_OK) return rc;
+  ctx->cursor = p1;
+  return RFX_OK;
+}
+
+int rfx_render_finish(rfx_ctx * ctx)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  const uint64_t total = (uint64_t)ctx->W * ctx->H;
+  if (!ctx->inProgress) return RFX_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->lastStream ? ctx->lastStream : ctx->stream;
+  int rc;
+  if (ctx->cursor < total && (rc = skipPixels(ctx, ctx->cursor, total, st)) != RFX_OK) return rc;
+  ctx->cursor = total;
+  ctx->inProgress = false;
+  return RFX_OK;
+}
+
+int rfx_buffer_alloc(rfx_ctx * ctx, uint64_t bytes, void ** device_ptr)
+{
+  if (!ctx || !device_ptr || !bytes) return fail(ctx, RFX_ERR_ARG, "rfx_buffer_alloc: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMalloc(device_ptr, bytes));
+  CK(cudaMemset(*device_ptr, 0, bytes));
+  return RFX_OK;
+}
+
+int rfx_buffer_free(rfx_ctx * ctx, void * device_ptr)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaFree(device_ptr));
+  return RFX_OK;
+}
+
+int rfx_buffer_read(rfx_ctx * ctx, const void * device_ptr, void * host_dst, uint64_t bytes)
+{
+  if (!ctx || !device_ptr || !host_dst) return fail(ctx, RFX_ERR_ARG, "rfx_buffer_read: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(host_dst, device_ptr, bytes, cudaMemcpyDeviceToHost));
+  ctx->stats.d2h_bytes += bytes;
+  return RFX_OK;
+}
+
+int rfx_ipc_export(rfx_ctx * ctx, void * device_ptr, unsigned char handle[64])
+{
+  if (!ctx || !device_ptr || !handle) return fail(ctx, RFX_ERR_ARG, "rfx_ipc_export: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, device_ptr));
+  memcpy(handle, &h, 64);
+  return RFX_OK;
+}
+
+int rfx_ipc_import(rfx_ctx * ctx, const unsigned char handle[64], void ** device_ptr)
+{
+  if (!ctx || !device_ptr || !handle) return fail(ctx, RFX_ERR_ARG, "rfx_ipc_import: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CK(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return RFX_OK;
+}
+
+int rfx_ipc_close(rfx_ctx * ctx, void * device_ptr)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaIpcCloseMemHandle(device_ptr));
+  return RFX_OK;
+}
+
 float rfx_progress(const rfx_ctx * ctx)
 {
   if (!ctx || !ctx->W || !ctx->H) return 0.0f;
@@ -727,8 +841,9 @@ float rfx_progress(const rfx_ctx * ctx)
 int rfx_additive_counter(const rfx_ctx * ctx) { return ctx ? ctx->additiveCounter : 0; }
 int rfx_in_progress(const rfx_ctx * ctx) { return ctx && ctx->inProgress ? 1 : 0; }
 
-static int readResolved(rfx_ctx * ctx, float * rgbf, uint32_t * argb)
+static int readResolved(rfx_ctx * ctx, float * rgbf, uint32_t * argb, int divide = 1)
 {
+  const int counter = divide ? ctx->additiveCounter : 0;
   if (!ctx->W || !ctx->H) return fail(ctx, RFX_ERR_ARG, "image size not set");
   CK(cudaSetDevice(ctx->device));
   int rc;
@@ -737,19 +852,19 @@ static int readResolved(rfx_ctx * ctx, float * rgbf, uint32_t * argb)
   if (argb)
   {
     if ((rc = ensure(ctx, ctx->dFrame[0], ctx->frameCap, n)) != RFX_OK) return rc;
-    ctx->stats.kernel_launches += launchResolve(ctx->dImage, n, ctx->additiveCounter, nullptr, ctx->dFrame[0], ctx->stream);
+    ctx->stats.kernel_launches += launchResolve(ctx->dImage, n, counter, nullptr, ctx->dFrame[0], ctx->stream);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(argb, ctx->dFrame[0], n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.d2h_bytes += n * 4;
   }
   if (rgbf)
   {
-    if (ctx->additiveCounter > 1)
+    if (counter > 1)
     {
       // divide on the device into the ranked-state scratch (reused as a float buffer), then copy
       size_t need = n * 3;
       if ((rc = ensure(ctx, ctx->dSampleStates, ctx->statesCap, need)) != RFX_OK) return rc;
-      ctx->stats.kernel_launches += launchResolve(ctx->dImage, n, ctx->additiveCounter, reinterpret_cast<float *>(ctx->dSampleStates), nullptr, ctx->stream);
+      ctx->stats.kernel_launches += launchResolve(ctx->dImage, n, counter, reinterpret_cast<float *>(ctx->dSampleStates), nullptr, ctx->stream);
       CK(cudaGetLastError());
       CK(cudaMemcpyAsync(rgbf, ctx->dSampleStates, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -771,6 +886,37 @@ int rfx_read_rgbf(rfx_ctx * ctx, float * dst)
 {
   if (!ctx || !dst) return fail(ctx, RFX_ERR_ARG, "rfx_read_rgbf: NULL argument");
   return readResolved(ctx, dst, nullptr);
+}
+
+int rfx_read_image(rfx_ctx * ctx, float * rgbf, uint32_t * argb, int divide)
+{
+  if (!ctx || (!rgbf && !argb)) return fail(ctx, RFX_ERR_ARG, "rfx_read_image: NULL argument");
+  return readResolved(ctx, rgbf, argb, divide);
+}
+
+int rfx_trace_rays(rfx_ctx * ctx, int n, const float * origins, const float * rays, int reflect_num, float * rgb)
+{
+  if (!ctx || n < 0 || !origins || !rays || !rgb || reflect_num <= 0) return fail(ctx, RFX_ERR_ARG, "rfx_trace_rays: bad argument");
+  if (n == 0) return RFX_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int rc;
+  if ((rc = useStream(ctx, st)) != RFX_OK) return rc;
+  if ((rc = uploadScene(ctx, st)) != RFX_OK) return rc;
+  if ((rc = rankSamples(ctx, (uint64_t)n, false, st)) != RFX_OK) return rc;
+  // ray buffers: origins | rays | rgb in one scratch allocation
+  if ((rc = ensure(ctx, ctx->dRays, ctx->raysCap, (size_t)n * 9)) != RFX_OK) return rc;
+  float * dO = ctx->dRays, * dR = ctx->dRays + (size_t)n * 3, * dC = ctx->dRays + (size_t)n * 6;
+  CK(cudaMemcpyAsync(dO, origins, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dR, rays, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+  ctx->stats.h2d_bytes += (uint64_t)n * 24;
+  ctx->stats.kernel_launches += launchTraceRays(ctx->dBlob, ctx->blobBytes, n, dO, dR, reflect_num, ctx->dSampleStates, dC, ctx->dCounters, st);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(rgb, dC, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  ctx->stats.d2h_bytes += (uint64_t)n * 12;
+  ctx->stats.samples += (uint64_t)n;
+  return checkStatus(ctx);
 }
 
 int rfx_read_pixel(rfx_ctx * ctx, int x, int y, float rgb[3])

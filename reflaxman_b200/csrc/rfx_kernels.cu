@@ -603,6 +603,58 @@ int launchTrace(const TraceWork & w, cudaStream_t st)
 }
 
 // =====================================================================================================================
+// Scene::trace for an explicit ray list (rfx_trace_rays)
+// =====================================================================================================================
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(const unsigned char * __restrict__ sceneBlob, uint32_t sceneBytes, int n,
+                                                              const float * __restrict__ origins, const float * __restrict__ rays, int reflNum,
+                                                              const uint32_t * __restrict__ sampleStates, float * __restrict__ rgbOut,
+                                                              unsigned long long * __restrict__ counters)
+{
+  extern __shared__ uint4 smemBlob[];
+  {
+    const uint4 * src = reinterpret_cast<const uint4 *>(sceneBlob);
+    for (uint32_t i = threadIdx.x; i < sceneBytes / 16; i += blockDim.x) smemBlob[i] = src[i];
+  }
+  __syncthreads();
+  const SceneView sc = makeView(reinterpret_cast<const unsigned char *>(smemBlob));
+  uint32_t nBounces = 0, nShadow = 0, sig = 2166136261u;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+  {
+    uint32_t s = sampleStates[i];
+    V3 rd;
+    rngTriple(s, rd.x, rd.y, rd.z);
+    const V3 c = traceSample(sc, mk(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]), mk(rays[3 * i], rays[3 * i + 1], rays[3 * i + 2]),
+                             reflNum, rd, nBounces, nShadow, sig);
+    rgbOut[3 * i] = c.x; rgbOut[3 * i + 1] = c.y; rgbOut[3 * i + 2] = c.z;
+  }
+  const uint32_t wb = __reduce_add_sync(0xffffffffu, nBounces);
+  const uint32_t ws = __reduce_add_sync(0xffffffffu, nShadow);
+  if ((threadIdx.x & 31) == 0 && counters)
+  {
+    const uint32_t slot = (blockIdx.x * (TRACE_THREADS / 32) + (threadIdx.x >> 5)) & 31u;
+    atomicAdd(&counters[slot * 2], (unsigned long long)wb);
+    atomicAdd(&counters[slot * 2 + 1], (unsigned long long)ws);
+  }
+}
+
+int launchTraceRays(const void * sceneBlob, uint32_t sceneBytes, int n, const float * origins, const float * rays, int reflNum,
+                    const uint32_t * sampleStates, float * rgbOut, unsigned long long * counters, cudaStream_t st)
+{
+  if (n <= 0) return 0;
+  const uint32_t smem = (sceneBytes + 15u) & ~15u;
+  static uint32_t optedIn = 0;
+  if (smem > 48 * 1024 && smem > optedIn)
+  {
+    cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    optedIn = smem;
+  }
+  k_trace_rays<<<(n + TRACE_THREADS - 1) / TRACE_THREADS, TRACE_THREADS, smem, st>>>(reinterpret_cast<const unsigned char *>(sceneBlob), smem, n,
+                                                                                      origins, rays, reflNum, sampleStates, rgbOut, counters);
+  return 1;
+}
+
+// =====================================================================================================================
 // K3: imagePixel() + argb() for the whole image (reference Render.cpp:103-114, Color.cpp:114-117)
 // =====================================================================================================================
 __global__ void __launch_bounds__(256) k_resolve(const float * __restrict__ image, unsigned long long nPixels, int additiveCounter,

@@ -47,6 +47,10 @@ struct TraceWork
 int launchTrace(const TraceWork & w, cudaStream_t st);                              // any scene: shared-memory resident blob
 int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st);   // small scenes: constant-bank resident
 
+// Scene::trace for a list of rays (rfx_trace_rays): rays[i] uses sampleStates[i]
+int launchTraceRays(const void * sceneBlob, uint32_t sceneBytes, int n, const float * origins, const float * rays, int reflNum,
+                    const uint32_t * sampleStates, float * rgbOut, unsigned long long * counters, cudaStream_t st);
+
 // ---- K3: resolve (imagePixel + argb) ---------------------------------------------------------------------------
 int launchResolve(const float * image, uint64_t nPixels, int additiveCounter, float * rgbfOut, uint32_t * argbOut, cudaStream_t st);
 int launchClear(float * image, uint64_t nFloats, cudaStream_t st);

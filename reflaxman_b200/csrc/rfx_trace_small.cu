@@ -358,13 +358,14 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
   }
   else if (tiled)
   {
-    // whole-frame slice: 8x4 pixel tile per warp
+    // row-aligned slice (a whole frame or a band of rows): 8x4 pixel tile per warp
     const uint32_t tilesX = (fp.W + 7u) >> 3;
+    const uint32_t y0 = (uint32_t)(fp.p0 / fp.W), y1 = (uint32_t)(fp.p1 / fp.W);
     const uint32_t warp = (uint32_t)(gid >> 5), lane = threadIdx.x & 31u;
     x = (warp % tilesX) * 8u + (lane & 7u);
-    y = (warp / tilesX) * 4u + (lane >> 3);
-    valid = x < fp.W && y < fp.H;
-    firstState = ((uint64_t)y * fp.W + x) * (uint64_t)(sn * sn);
+    y = y0 + (warp / tilesX) * 4u + (lane >> 3);
+    valid = x < fp.W && y < y1;
+    firstState = (((uint64_t)y * fp.W + x) - fp.p0) * (uint64_t)(sn * sn);
   }
   else
   {
@@ -456,10 +457,11 @@ int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st
   int tiled = 0;
   if (fp.sampleNum > 0)
   {
-    if (fp.p0 == 0 && fp.p1 == (uint64_t)fp.W * fp.H)
+    if (fp.p0 % fp.W == 0 && fp.p1 % fp.W == 0)
     {
       tiled = 1;
-      nThreads = (uint64_t)((fp.W + 7) / 8) * ((fp.H + 3) / 4) * 32;
+      const uint64_t rows = (fp.p1 - fp.p0) / fp.W;
+      nThreads = (uint64_t)((fp.W + 7) / 8) * ((rows + 3) / 4) * 32;
     }
     else
       nThreads = fp.p1 - fp.p0;

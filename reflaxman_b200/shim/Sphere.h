@@ -1,0 +1,3 @@
+// drop-in replacement for the reference's src/common/Sphere.h: the B200 shim (rfx_shim.hpp) provides the class surface
+#pragma once
+#include "rfx_shim.hpp"
