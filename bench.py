@@ -342,5 +342,9 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload in ("config3", "config4", "config5"):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_extra
+        getattr(bench_extra, a.workload)(a)
     else:
         run_ours(a)
