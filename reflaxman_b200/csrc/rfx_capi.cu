@@ -103,6 +103,7 @@ struct rfx_ctx
   int rngSlot = 0;
   uint32_t seedRender = 12345u;
   uint32_t * dBlockCounts = nullptr, * dBlockOffsets = nullptr; size_t blocksCap = 0, offsCap = 0;
+  uint8_t * dAcceptMasks = nullptr; size_t masksCap = 0;
   uint32_t * dSampleStates = nullptr; size_t statesCap = 0;
   int * dStatus = nullptr;
   float * dRays = nullptr; size_t raysCap = 0;   // rfx_trace_rays scratch
@@ -300,12 +301,14 @@ int rankSamples(rfx_ctx * ctx, uint64_t n, bool skipOnly, cudaStream_t st)
   int rc;
   if ((rc = ensure(ctx, ctx->dBlockCounts, ctx->blocksCap, nBlocks)) != RFX_OK) return rc;
   if ((rc = ensure(ctx, ctx->dBlockOffsets, ctx->offsCap, nBlocks)) != RFX_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dAcceptMasks, ctx->masksCap, (size_t)nBlocks * RNG_THREADS)) != RFX_OK) return rc;
   if (!skipOnly && (rc = ensure(ctx, ctx->dSampleStates, ctx->statesCap, n)) != RFX_OK) return rc;
   RngWork w;
   w.stateIn = ctx->dRng + ctx->rngSlot;
   w.stateOut = ctx->dRng + (ctx->rngSlot ^ 1);
   w.blockCounts = ctx->dBlockCounts;
   w.blockOffsets = ctx->dBlockOffsets;
+  w.acceptMasks = ctx->dAcceptMasks;
   w.sampleStates = skipOnly ? nullptr : ctx->dSampleStates;
   w.status = ctx->dStatus;
   w.n = n;
@@ -319,7 +322,9 @@ int rankSamples(rfx_ctx * ctx, uint64_t n, bool skipOnly, cudaStream_t st)
 const uint64_t MAX_CALLS_PER_LAUNCH = 1ull << 25;   // bounds the ranked-state scratch (128 MB) for huge SSAA factors / 8K frames
 
 // render pixels [p0, p1) of the frame latched by render_begin
-int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, bool writeImage, cudaStream_t st)
+// preStates: random states already ranked for exactly [p0, p1) (batch path ranks several frames per K1 pass); NULL = rank here
+int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, bool writeImage, cudaStream_t st,
+                const uint32_t * preStates = nullptr)
 {
   int rc;
   const int sn = ctx->sampleNum;
@@ -332,7 +337,7 @@ int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, boo
       const uint64_t per = (uint64_t)sn * sn;
       uint64_t pix = MAX_CALLS_PER_LAUNCH / per;
       if (pix < 1) pix = 1;
-      end = std::min(p1, cur + pix);
+      end = preStates ? p1 : std::min(p1, cur + pix);
       nCalls = (end - cur) * per;
     }
     else
@@ -344,14 +349,14 @@ int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, boo
     }
     if (nCalls > 0)
     {
-      if ((rc = rankSamples(ctx, nCalls, false, st)) != RFX_OK) return rc;
+      if (!preStates && (rc = rankSamples(ctx, nCalls, false, st)) != RFX_OK) return rc;
       TraceWork w;
       w.sceneBlob = ctx->dBlob;
       w.sceneBytes = ctx->blobBytes;
       w.fp = ctx->snap;
       w.fp.p0 = cur; w.fp.p1 = end; w.fp.firstRank = firstRank;
       w.fp.seedRender = ctx->seedRender;
-      w.sampleStates = ctx->dSampleStates;
+      w.sampleStates = preStates ? preStates : ctx->dSampleStates;
       w.image = writeImage ? ctx->dImage : nullptr;
       w.argbOut = argbOut;
       w.sigOut = ctx->sigOn ? ctx->dSig : nullptr;
@@ -454,7 +459,7 @@ void rfx_destroy(rfx_ctx * ctx)
   for (HostTex & t : ctx->tex) if (t.dev) cudaFree(t.dev);
   cudaFree(ctx->dBlob); cudaFree(ctx->dLut); cudaFree(ctx->dImage); cudaFree(ctx->dSig); cudaFree(ctx->dRng);
   cudaFree(ctx->dBlockCounts); cudaFree(ctx->dBlockOffsets); cudaFree(ctx->dSampleStates); cudaFree(ctx->dStatus);
-  cudaFree(ctx->dCounters); cudaFree(ctx->dRays);
+  cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dAcceptMasks);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   for (int i = 0; i < 3; i++)
   {
@@ -977,12 +982,24 @@ int rfx_render_frames_device(rfx_ctx * ctx, int n_frames, const float * cams, in
   if ((rc = useStream(ctx, st)) != RFX_OK) return rc;
   if ((rc = uploadScene(ctx, st)) != RFX_OK) return rc;
   const uint64_t total = (uint64_t)ctx->W * ctx->H;
-  for (int f = 0; f < n_frames; f++)
+  // one K1 pass ranks the random states of a whole group of frames (the stream simply continues from frame to frame)
+  if (reflect_num <= 0 || sample_num == 0) return fail(ctx, RFX_ERR_ARG, "rfx_render_frames_device: reflect_num must be > 0 and sample_num != 0");
+  ctx->sampleNum = sample_num;
+  const uint64_t perFrame = callsIn(ctx, 0, total);
+  const int group = (int)std::max<uint64_t>(1, MAX_CALLS_PER_LAUNCH / std::max<uint64_t>(perFrame, 1));
+  for (int f0 = 0; f0 < n_frames; f0 += group)
   {
-    if ((rc = beginFrame(ctx, cams + 13 * (size_t)f, reflect_num, sample_num)) != RFX_OK) return rc;
-    if ((rc = renderRange(ctx, 0, total, argb_device + (size_t)f * total, false, st)) != RFX_OK) return rc;
-    ctx->cursor = total;
-    ctx->inProgress = false;
+    const int g = std::min(group, n_frames - f0);
+    const bool pre = perFrame <= MAX_CALLS_PER_LAUNCH;
+    if (pre && (rc = rankSamples(ctx, perFrame * g, false, st)) != RFX_OK) return rc;
+    for (int f = f0; f < f0 + g; f++)
+    {
+      if ((rc = beginFrame(ctx, cams + 13 * (size_t)f, reflect_num, sample_num)) != RFX_OK) return rc;
+      if ((rc = renderRange(ctx, 0, total, argb_device + (size_t)f * total, false, st,
+                            pre ? ctx->dSampleStates + (size_t)(f - f0) * perFrame : nullptr)) != RFX_OK) return rc;
+      ctx->cursor = total;
+      ctx->inProgress = false;
+    }
   }
   return RFX_OK;
 }
@@ -1010,12 +1027,19 @@ int rfx_render_frames(rfx_ctx * ctx, int n_frames, const float * cams, int refle
       break;
     }
   }
+  if (reflect_num <= 0 || sample_num == 0) return fail(ctx, RFX_ERR_ARG, "rfx_render_frames: reflect_num must be > 0 and sample_num != 0");
+  ctx->sampleNum = sample_num;
+  const uint64_t perFrame = callsIn(ctx, 0, total);
+  const int group = (int)std::max<uint64_t>(1, MAX_CALLS_PER_LAUNCH / std::max<uint64_t>(perFrame, 1));
+  const bool pre = perFrame <= MAX_CALLS_PER_LAUNCH;
   for (int f = 0; f < n_frames; f++)
   {
     const int slot = f % 3;
+    if (pre && f % group == 0 && (rc = rankSamples(ctx, perFrame * std::min(group, n_frames - f), false, st)) != RFX_OK) return rc;
     if (f >= 3) CK(cudaStreamWaitEvent(st, ctx->evCopied[slot], 0));   // slot free again?
     if ((rc = beginFrame(ctx, cams + 13 * (size_t)f, reflect_num, sample_num)) != RFX_OK) return rc;
-    if ((rc = renderRange(ctx, 0, total, ctx->dFrame[slot], false, st)) != RFX_OK) return rc;
+    if ((rc = renderRange(ctx, 0, total, ctx->dFrame[slot], false, st,
+                          pre ? ctx->dSampleStates + (size_t)(f % group) * perFrame : nullptr)) != RFX_OK) return rc;
     ctx->cursor = total;
     ctx->inProgress = false;
     CK(cudaEventRecord(ctx->evRendered[slot], st));

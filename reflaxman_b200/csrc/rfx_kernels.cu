@@ -32,18 +32,21 @@ namespace rfx
 
 uint32_t lcgJumpHost(uint32_t s, uint64_t n) { return lcgJump(s, (uint32_t)n); }
 
-__global__ void __launch_bounds__(RNG_THREADS) k_rng_count(const uint32_t * __restrict__ stateIn, uint32_t * __restrict__ blockCounts)
+__global__ void __launch_bounds__(RNG_THREADS) k_rng_count(const uint32_t * __restrict__ stateIn, uint32_t * __restrict__ blockCounts,
+                                                           uint8_t * __restrict__ acceptMasks)
 {
   __shared__ int warpSums[RNG_THREADS / 32];
   const uint32_t gid = blockIdx.x * RNG_THREADS + threadIdx.x;
   uint32_t s = lcgJump(*stateIn, gid * (3u * RNG_TRIPLES_PER_THREAD));
-  int cnt = 0;
+  uint32_t mask = 0;
 #pragma unroll
   for (int k = 0; k < RNG_TRIPLES_PER_THREAD; k++)
   {
     float x, y, z;
-    cnt += rngTriple(s, x, y, z) ? 1 : 0;
+    if (rngTriple(s, x, y, z)) mask |= 1u << k;
   }
+  acceptMasks[gid] = (uint8_t)mask;   // the scatter pass re-walks the integer LCG only; the float accept test runs once
+  int cnt = __popc(mask);
   cnt = __reduce_add_sync(0xffffffffu, cnt);
   if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = cnt;
   __syncthreads();
@@ -56,38 +59,55 @@ __global__ void __launch_bounds__(RNG_THREADS) k_rng_count(const uint32_t * __re
   }
 }
 
-// single-CTA exclusive scan of the per-block accept counts (a few thousand to a few hundred thousand entries)
+// single-CTA exclusive scan of the per-block accept counts (a few thousand to a few hundred thousand entries):
+// coalesced 1024-wide tiles, warp-shuffle scan inside each tile, running carry between tiles
 __global__ void __launch_bounds__(1024) k_rng_scan(const uint32_t * __restrict__ counts, uint32_t * __restrict__ offsets,
                                                    uint32_t nBlocks, unsigned long long n, int * status)
 {
-  __shared__ unsigned long long part[1024];
-  const uint32_t per = (nBlocks + 1023u) / 1024u;
-  const uint32_t b0 = threadIdx.x * per;
-  const uint32_t b1 = min(b0 + per, nBlocks);
-  unsigned long long sum = 0;
-  for (uint32_t b = b0; b < b1; b++) sum += counts[b];
-  part[threadIdx.x] = sum;
+  __shared__ uint32_t warpTot[32];
+  __shared__ unsigned long long carryS;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carryS = 0ull;
   __syncthreads();
-  // Hillis-Steele inclusive scan over 1024 partials
-  for (int off = 1; off < 1024; off <<= 1)
+  for (uint32_t base = 0; base < nBlocks; base += 1024u)
   {
-    unsigned long long v = (threadIdx.x >= off) ? part[threadIdx.x - off] : 0ull;
+    const uint32_t idx = base + threadIdx.x;
+    const uint32_t v = idx < nBlocks ? counts[idx] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1)
+    {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= (uint32_t)off) incl += t;
+    }
+    if (lane == 31u) warpTot[warp] = incl;
     __syncthreads();
-    part[threadIdx.x] += v;
+    const unsigned long long carry = carryS;
+    // every warp scans the 32 warp totals redundantly (cheaper than another barrier)
+    uint32_t wt = warpTot[lane], winc = wt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1)
+    {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, winc, off);
+      if (lane >= (uint32_t)off) winc += t;
+    }
+    const uint32_t warpBase = __shfl_sync(0xffffffffu, winc - wt, warp);
+    const uint32_t tileTotal = __shfl_sync(0xffffffffu, winc, 31);
+    if (idx < nBlocks)
+    {
+      // offsets saturate at 2^32-1: any block whose offset is >= n is skipped by the scatter pass anyway
+      const unsigned long long o = carry + warpBase + (incl - v);
+      offsets[idx] = o > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)o;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carryS = carry + tileTotal;
     __syncthreads();
   }
-  unsigned long long run = part[threadIdx.x] - sum;
-  for (uint32_t b = b0; b < b1; b++)
-  {
-    // offsets saturate at 2^32-1: any block whose offset is >= n is skipped by the scatter pass anyway
-    offsets[b] = run > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)run;
-    run += counts[b];
-  }
-  if (threadIdx.x == 1023 && part[1023] < n) *status = 1;
+  if (threadIdx.x == 0 && carryS < n) *status = 1;
 }
 
 __global__ void __launch_bounds__(RNG_THREADS) k_rng_scatter(const uint32_t * __restrict__ stateIn, uint32_t * __restrict__ stateOut,
-                                                             const uint32_t * __restrict__ blockOffsets,
+                                                             const uint32_t * __restrict__ blockOffsets, const uint8_t * __restrict__ acceptMasks,
                                                              uint32_t * __restrict__ sampleStates, unsigned long long n, uint32_t rankBase)
 {
   __shared__ int warpSums[RNG_THREADS / 32];
@@ -97,13 +117,7 @@ __global__ void __launch_bounds__(RNG_THREADS) k_rng_scatter(const uint32_t * __
   const uint32_t gid = blockIdx.x * RNG_THREADS + threadIdx.x;
   const uint32_t sStart = lcgJump(*stateIn, gid * (3u * RNG_TRIPLES_PER_THREAD));
   uint32_t s = sStart;
-  uint32_t mask = 0;
-#pragma unroll
-  for (int k = 0; k < RNG_TRIPLES_PER_THREAD; k++)
-  {
-    float x, y, z;
-    if (rngTriple(s, x, y, z)) mask |= 1u << k;
-  }
+  const uint32_t mask = acceptMasks[gid];
   const int cnt = __popc(mask);
   // block-wide exclusive scan of cnt
   int incl = cnt;
@@ -148,9 +162,9 @@ uint32_t rngBlocksFor(uint64_t n)
 
 int launchRngRank(const RngWork & w, cudaStream_t st)
 {
-  k_rng_count<<<w.nBlocks, RNG_THREADS, 0, st>>>(w.stateIn, w.blockCounts);
+  k_rng_count<<<w.nBlocks, RNG_THREADS, 0, st>>>(w.stateIn, w.blockCounts, w.acceptMasks);
   k_rng_scan<<<1, 1024, 0, st>>>(w.blockCounts, w.blockOffsets, w.nBlocks, (unsigned long long)w.n, w.status);
-  k_rng_scatter<<<w.nBlocks, RNG_THREADS, 0, st>>>(w.stateIn, w.stateOut, w.blockOffsets, w.sampleStates, (unsigned long long)w.n, 0u);
+  k_rng_scatter<<<w.nBlocks, RNG_THREADS, 0, st>>>(w.stateIn, w.stateOut, w.blockOffsets, w.acceptMasks, w.sampleStates, (unsigned long long)w.n, 0u);
   return 3;
 }
 
@@ -501,8 +515,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, RFX_BIG_MINBLOCKS) k_trace(cons
       if (fp.jitter)
       {
         uint32_t s = lcgJump(fp.seedRender, (uint32_t)(2 * gid));      // two draws per pixel, Render.cpp:177-178
-        s = 214013u * s + 2531011u; rndx = float((int)((s >> 16) & 0x7FFFu)) / float(0x7FFF);
-        s = 214013u * s + 2531011u; rndy = float((int)((s >> 16) & 0x7FFFu)) / float(0x7FFF);
+        s = 214013u * s + 2531011u; rndx = divExact(float((int)((s >> 16) & 0x7FFFu)), 32767.0f, RFX_RCP_32767);
+        s = 214013u * s + 2531011u; rndy = divExact(float((int)((s >> 16) & 0x7FFFu)), 32767.0f, RFX_RCP_32767);
       }
       V3 fin = mk(0.0f, 0.0f, 0.0f);
       uint32_t sig = 2166136261u;

@@ -22,6 +22,7 @@ struct RngWork
   uint32_t * stateOut;          // device: LCG state after the triple that holds rank n-1
   uint32_t * blockCounts;       // device scratch [nBlocks]
   uint32_t * blockOffsets;      // device scratch [nBlocks]
+  uint8_t * acceptMasks;        // device scratch [nBlocks * RNG_THREADS]: 8 accept bits per thread, count -> scatter
   uint32_t * sampleStates;      // device out [n] (may be NULL: skip-only)
   int * status;                 // device: set to 1 when fewer than n triples were accepted in nBlocks blocks
   uint64_t n;                   // accepted triples wanted

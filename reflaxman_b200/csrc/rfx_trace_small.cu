@@ -9,7 +9,7 @@
 //     whole warp (warp-uniform object index), so the expensive sqrt/divide path is entered once per distinct
 //     candidate object per warp instead of once per loop iteration per lane.
 //   * The same routine answers closest-hit and shadow (any-hit) queries.
-//   * Warps own 8x4 pixel tiles (coherent primary/secondary rays, 32-byte ARGB row segments per store).
+//   * Warps own 4x8 pixel tiles of row-aligned slices (coherent primary/secondary rays; 8x4, 16x2, 32x1 measured slower).
 //   * The bounce recursion is the reference's own bounded iterative loop carrying throughput (mulColor).
 //
 // ARITHMETIC CONTRACT: compiled with --fmad=false, no fast-math: every + - * / sqrtf is the IEEE binary32 RN
@@ -27,6 +27,10 @@ namespace rfx
 #ifndef RFX_SMALL_UNROLL
 #define RFX_SMALL_UNROLL 0
 #endif
+#ifndef RFX_TILE_W
+#define RFX_TILE_W 4u      // pixel tile of one warp: RFX_TILE_W x RFX_TILE_H = 32 (4x8 measured best, profiles/variants_d_r1.jsonl)
+#endif
+#define RFX_TILE_H (32u / RFX_TILE_W)
 #ifndef RFX_SMALL_THREADS
 #define RFX_SMALL_THREADS 256
 #endif
@@ -88,7 +92,14 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
   const float a4 = 4.0f * a, a2 = 2.0f * a;                           // Sphere.cpp:53,57
   uint32_t mask = 0;
 
-#if RFX_SMALL_UNROLL
+#if RFX_SMALL_UNROLL == 2
+  // experiment: counts fixed at compile time -> straight-line code, immediate constant-bank offsets, no indirect branch
+#pragma unroll
+  for (int i = 0; i < RFX_FIX_NS; i++) RFX_SPHERE_REJECT(i)
+  if (!(a > RFX_VSN)) mask = 0;
+#pragma unroll
+  for (int k = 0; k < RFX_FIX_NT; k++) RFX_TRI_REJECT(k)
+#elif RFX_SMALL_UNROLL
   switch (sc.nS)   // fall-through: straight-line code for exactly nS spheres
   {
   case 16: RFX_SPHERE_REJECT(15)
@@ -126,11 +137,30 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
 #else
   // rolled: a ~20-instruction body that stays resident in the L0 instruction cache; the loop index is warp-uniform,
   // so sc.sph[i] is a uniform constant-bank load feeding uniform-register operands
+  {
+    uint32_t bit = 1u;
+    const uint32_t endBit = 1u << sc.nS;
 #pragma unroll 1
-  for (int i = 0; i < sc.nS; i++) RFX_SPHERE_REJECT(i)
-  if (!(a > RFX_VSN)) mask = 0;                                       // Sphere.cpp:55 `a > VERY_SMALL_NUMBER`
+    for (int i = 0; bit != endBit; i++, bit += bit)
+    {
+      const float vx = o.x - sc.sph[i].x, vy = o.y - sc.sph[i].y, vz = o.z - sc.sph[i].z;
+      const float b = (r2x * vx + r2y * vy) + r2z * vz;
+      const float c = ((vx * vx + vy * vy) + vz * vz) - sc.sph[i].w;
+      const float disc = b * b - a4 * c;
+      if (disc >= 0.0f) mask |= bit;
+    }
+    if (!(a > RFX_VSN)) mask = 0;                                     // Sphere.cpp:55 `a > VERY_SMALL_NUMBER`
+    bit = 1u << SM_TRI_BIT;
+    const uint32_t endTri = bit << sc.nT;
 #pragma unroll 1
-  for (int k = 0; k < sc.nT; k++) RFX_TRI_REJECT(k)
+    for (int k = 0; bit != endTri; k++, bit += bit)
+    {
+      const float px = o.x - sc.tri[k].v0[0], py = o.y - sc.tri[k].v0[1], pz = o.z - sc.tri[k].v0[2];
+      const float oz = (px * sc.tri[k].ax[6] + py * sc.tri[k].ax[7]) + pz * sc.tri[k].ax[8];
+      const float rz = (d.x * sc.tri[k].ax[6] + d.y * sc.tri[k].ax[7]) + d.z * sc.tri[k].ax[8];
+      if (fabsf(rz) > RFX_VSN && ((oz < 0.0f && rz > 0.0f) || (oz > 0.0f && rz < 0.0f))) mask |= bit;
+    }
+  }
 #endif
   for (int k = 0; k < sc.nP; k++) mask |= 1u << (SM_PLANE_BIT + k);   // planes are unreachable through the reference's Scene: no reject stage
   mask &= ~skipMask;
@@ -359,11 +389,11 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
   else if (tiled)
   {
     // row-aligned slice (a whole frame or a band of rows): 8x4 pixel tile per warp
-    const uint32_t tilesX = (fp.W + 7u) >> 3;
+    const uint32_t tilesX = (fp.W + (RFX_TILE_W - 1u)) / RFX_TILE_W;
     const uint32_t y0 = (uint32_t)(fp.p0 / fp.W), y1 = (uint32_t)(fp.p1 / fp.W);
     const uint32_t warp = (uint32_t)(gid >> 5), lane = threadIdx.x & 31u;
-    x = (warp % tilesX) * 8u + (lane & 7u);
-    y = y0 + (warp / tilesX) * 4u + (lane >> 3);
+    x = (warp % tilesX) * RFX_TILE_W + (lane % RFX_TILE_W);
+    y = y0 + (warp / tilesX) * RFX_TILE_H + (lane / RFX_TILE_W);
     valid = x < fp.W && y < y1;
     firstState = (((uint64_t)y * fp.W + x) - fp.p0) * (uint64_t)(sn * sn);
   }
@@ -384,8 +414,8 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
     if (fp.jitter && !blockMode)
     {
       uint32_t s = lcgJump(fp.seedRender, (uint32_t)(2 * (p - fp.p0)));      // two draws per pixel, Render.cpp:177-178
-      s = 214013u * s + 2531011u; rndx = float((int)((s >> 16) & 0x7FFFu)) / float(0x7FFF);
-      s = 214013u * s + 2531011u; rndy = float((int)((s >> 16) & 0x7FFFu)) / float(0x7FFF);
+      s = 214013u * s + 2531011u; rndx = divExact(float((int)((s >> 16) & 0x7FFFu)), 32767.0f, RFX_RCP_32767);
+      s = 214013u * s + 2531011u; rndy = divExact(float((int)((s >> 16) & 0x7FFFu)), 32767.0f, RFX_RCP_32767);
     }
     V3 fin = mk(0.0f, 0.0f, 0.0f);
     uint32_t sig = 2166136261u;
@@ -461,7 +491,7 @@ int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st
     {
       tiled = 1;
       const uint64_t rows = (fp.p1 - fp.p0) / fp.W;
-      nThreads = (uint64_t)((fp.W + 7) / 8) * ((rows + 3) / 4) * 32;
+      nThreads = (uint64_t)((fp.W + RFX_TILE_W - 1) / RFX_TILE_W) * ((rows + RFX_TILE_H - 1) / RFX_TILE_H) * 32;
     }
     else
       nThreads = fp.p1 - fp.p0;

@@ -90,3 +90,37 @@ def test_rand_dirs_parallel_model(oracle):
     assert np.array_equal(v[acc[:n]].view(np.uint32), dirs.view(np.uint32))
     assert int(st[3 * (acc[n - 1] + 1)]) == end_state
     assert abs(len(acc) / (m // 3) - 0.5236) < 0.01
+
+
+def test_constant_division_is_exact():
+    """rfx_device.cuh::divExact — q0 = RN(r*c), rem = fma(-q0, D, r), q = fma(rem, c, q0) with c = RN(1/D) — equals the
+    correctly rounded r / D on the whole input domain of each call site (exact rational arithmetic, exhaustive)."""
+    from fractions import Fraction
+    import math
+
+    def rn32(x):
+        if x == 0:
+            return Fraction(0)
+        sgn = -1 if x < 0 else 1
+        x = abs(x)
+        e = math.floor(math.log2(x))
+        while Fraction(2) ** e > x:
+            e -= 1
+        while Fraction(2) ** (e + 1) <= x:
+            e += 1
+        ulp = Fraction(2) ** (e - 23)
+        q = x / ulp
+        n = q.numerator // q.denominator
+        r = q - n
+        if r > Fraction(1, 2) or (r == Fraction(1, 2) and (n & 1)):
+            n += 1
+        return sgn * n * ulp
+
+    for D, hi, c_src in ((Fraction(32767, 2), 32768, 6.103701889514923e-05), (Fraction(32767), 32768, 3.0518509447574615e-05)):
+        c = rn32(1 / D)
+        assert float(c) == float(np.float32(c_src))          # the literal in rfx_device.cuh is RN(1/D)
+        for r in range(hi):
+            rf = Fraction(r)
+            q0 = rn32(rf * c)
+            rem = rn32(rf - q0 * D)
+            assert rn32(q0 + rem * c) == rn32(rf / D), (D, r)

@@ -11,15 +11,11 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 
 VARIANTS = {
     # name: (defines, force_path)
-    "small_rolled": (["RFX_SMALL_UNROLL=0"], 1),
-    "small_unrolled": (["RFX_SMALL_UNROLL=1"], 1),
-    "small_rolled_mb6": (["RFX_SMALL_UNROLL=0", "RFX_SMALL_MINBLOCKS=6"], 1),
-    "small_rolled_mb8": (["RFX_SMALL_UNROLL=0", "RFX_SMALL_MINBLOCKS=8"], 1),
-    "small_rolled_t64_mb12": (["RFX_SMALL_UNROLL=0", "RFX_SMALL_THREADS=64", "RFX_SMALL_MINBLOCKS=12"], 1),
-    "small_rolled_t256_mb3": (["RFX_SMALL_UNROLL=0", "RFX_SMALL_THREADS=256", "RFX_SMALL_MINBLOCKS=3"], 1),
-    "big": ([], 2),
-    "big_mb6": (["RFX_BIG_MINBLOCKS=6"], 2),
-    "big_mb8": (["RFX_BIG_MINBLOCKS=8"], 2),
+    "tile_8x4": (["RFX_TILE_W=8u"], 1),
+    "tile_4x8": (["RFX_TILE_W=4u"], 1),
+    "tile_16x2": (["RFX_TILE_W=16u"], 1),
+    "tile_32x1": (["RFX_TILE_W=32u"], 1),
+    "tile_2x16": (["RFX_TILE_W=2u"], 1),
 }
 
 
