@@ -78,6 +78,7 @@ SYMBOLS = [
     ("rfx_stats_reset", C.c_int, [C.c_void_p]),
     ("rfx_enable_profiling", C.c_int, [C.c_void_p, C.c_int]),
     ("rfx_force_path", C.c_int, [C.c_void_p, C.c_int]),
+    ("rfx_set_bvh_mode", C.c_int, [C.c_void_p, C.c_int]),
 ]
 
 _lib = None
@@ -318,6 +319,9 @@ class Context:
 
     def force_path(self, path):
         self._ck(self.L.rfx_force_path(self.h, path), "rfx_force_path")
+
+    def set_bvh_mode(self, mode):
+        self._ck(self.L.rfx_set_bvh_mode(self.h, mode), "rfx_set_bvh_mode")
 
     def device_info(self):
         d = RfxDeviceInfo()

@@ -29,7 +29,7 @@ struct HostObj
 {
   int kind;                 // 0 sphere, 1 triangle, 2 plane
   Material mat;             // order = insertion index
-  float center[3], sqRadius;
+  float center[3], sqRadius, radius;
   Triangle tri;
   Plane plane;
 };
@@ -66,6 +66,46 @@ void invertColumns(H3 u, H3 v, H3 n, float out[9])
 
 template <typename T> inline size_t align16(T v) { return ((size_t)v + 15) & ~(size_t)15; }
 
+// ---- bounding-volume hierarchy over the spheres of big scenes (SURVEY f-3) ---------------------------------------------
+// Median split on the widest centroid axis, leaves of <= 4 spheres, boxes inflated by `margin`.  The hierarchy only
+// selects which spheres receive the exact reference test on the device; it never decides a hit.
+struct BvhNode { float lo[3], hi[3]; int a, b; };
+struct BvhPrim { float c[3], r; int index; };
+
+int buildBvhRec(std::vector<BvhNode> & nodes, std::vector<BvhPrim> & prims, int begin, int end, float margin, int depth, int & maxDepth)
+{
+  const int me = (int)nodes.size();
+  nodes.push_back(BvhNode());
+  maxDepth = std::max(maxDepth, depth);
+  float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX }, clo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, chi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+  for (int i = begin; i < end; i++)
+    for (int k = 0; k < 3; k++)
+    {
+      lo[k] = std::min(lo[k], prims[i].c[k] - prims[i].r - margin);
+      hi[k] = std::max(hi[k], prims[i].c[k] + prims[i].r + margin);
+      clo[k] = std::min(clo[k], prims[i].c[k]);
+      chi[k] = std::max(chi[k], prims[i].c[k]);
+    }
+  BvhNode n;
+  memcpy(n.lo, lo, sizeof(lo)); memcpy(n.hi, hi, sizeof(hi));
+  if (end - begin <= 4)
+  {
+    n.a = begin; n.b = -(end - begin);
+    nodes[me] = n;
+    return me;
+  }
+  int axis = 0;
+  if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+  if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+  const int mid = (begin + end) / 2;
+  std::nth_element(prims.begin() + begin, prims.begin() + mid, prims.begin() + end,
+                   [axis](const BvhPrim & x, const BvhPrim & y) { return x.c[axis] < y.c[axis] || (x.c[axis] == y.c[axis] && x.index < y.index); });
+  n.a = buildBvhRec(nodes, prims, begin, mid, margin, depth + 1, maxDepth);
+  n.b = buildBvhRec(nodes, prims, mid, end, margin, depth + 1, maxDepth);
+  nodes[me] = n;
+  return me;
+}
+
 } // namespace
 
 struct rfx_ctx
@@ -88,6 +128,9 @@ struct rfx_ctx
   SmallScene small; bool smallOk = false;   // constant-bank form of the same scene, when it fits
   int forcePath = 0;                        // 0 auto, 1 small (constant bank), 2 big (shared memory) — tests exercise both
   float * dLut = nullptr;
+  float4 * dBvhNodes = nullptr; size_t bvhNodesCap = 0;   // big scenes only (see buildBvh)
+  int * dBvhPrims = nullptr; size_t bvhPrimsCap = 0;
+  int bvhMode = 0;                          // 0 auto (spheres > 32), 1 always, 2 never — tests compare both
 
   // ---- camera + render state (reference Render.h:9-27)
   float eye[3] = { 0, 0, 0 }, view[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, fov = 1.0f;
@@ -214,6 +257,48 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
   h.offTex = (uint32_t)off; off = align16(off + sizeof(TexRef) * ctx->tex.size());
   h.bytes = (uint32_t)off;
   h.byteLut = ctx->dLut;
+  h.bvhNodes = nullptr;
+  h.bvhPrims = nullptr;
+  const bool wantBvh = ctx->bvhMode == 1 ? !sph.empty() : ctx->bvhMode == 2 ? false : sph.size() > 32;
+  if (wantBvh)
+  {
+    std::vector<BvhPrim> prims(sph.size());
+    float extent = 1.0f;
+    for (size_t i = 0; i < sph.size(); i++)
+    {
+      BvhPrim & p = prims[i];
+      memcpy(p.c, sph[i]->center, sizeof(p.c));
+      p.r = sph[i]->radius;
+      p.index = (int)i;
+      for (int k = 0; k < 3; k++) extent = std::max(extent, fabsf(p.c[k]) + p.r);
+    }
+    // the exact sphere test is wrong by ~1e-6 of the scene extent at most; the boxes get three orders of magnitude more
+    const float margin = 1e-3f * extent;
+    std::vector<BvhNode> nodes;
+    int maxDepth = 0;
+    buildBvhRec(nodes, prims, 0, (int)prims.size(), margin, 0, maxDepth);
+    if (maxDepth < 30)   // traversal stack is 32 deep; a median split of < 2^30 spheres never gets here
+    {
+      std::vector<float4> packed(nodes.size() * 2);
+      std::vector<int> order(prims.size());
+      for (size_t i = 0; i < nodes.size(); i++)
+      {
+        float4 lo4 = make_float4(nodes[i].lo[0], nodes[i].lo[1], nodes[i].lo[2], 0.0f), hi4 = make_float4(nodes[i].hi[0], nodes[i].hi[1], nodes[i].hi[2], 0.0f);
+        memcpy(&lo4.w, &nodes[i].a, 4); memcpy(&hi4.w, &nodes[i].b, 4);
+        packed[2 * i] = lo4; packed[2 * i + 1] = hi4;
+      }
+      for (size_t i = 0; i < prims.size(); i++) order[i] = prims[i].index;
+      int rc;
+      if ((rc = ensure(ctx, ctx->dBvhNodes, ctx->bvhNodesCap, packed.size())) != RFX_OK) return rc;
+      if ((rc = ensure(ctx, ctx->dBvhPrims, ctx->bvhPrimsCap, order.size())) != RFX_OK) return rc;
+      CK(cudaMemcpyAsync(ctx->dBvhNodes, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->dBvhPrims, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      ctx->stats.h2d_bytes += packed.size() * sizeof(float4) + order.size() * sizeof(int);
+      h.bvhNodes = ctx->dBvhNodes;
+      h.bvhPrims = ctx->dBvhPrims;
+    }
+  }
   if (off > 200 * 1024) return fail(ctx, RFX_ERR_ARG, "scene too large for the shared-memory resident layout (200 KB)");
 
   std::vector<unsigned char> blob(off, 0);
@@ -459,7 +544,7 @@ void rfx_destroy(rfx_ctx * ctx)
   for (HostTex & t : ctx->tex) if (t.dev) cudaFree(t.dev);
   cudaFree(ctx->dBlob); cudaFree(ctx->dLut); cudaFree(ctx->dImage); cudaFree(ctx->dSig); cudaFree(ctx->dRng);
   cudaFree(ctx->dBlockCounts); cudaFree(ctx->dBlockOffsets); cudaFree(ctx->dSampleStates); cudaFree(ctx->dStatus);
-  cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dAcceptMasks);
+  cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dAcceptMasks); cudaFree(ctx->dBvhNodes); cudaFree(ctx->dBvhPrims);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   for (int i = 0; i < 3; i++)
   {
@@ -532,6 +617,7 @@ int rfx_add_sphere(rfx_ctx * ctx, const float c[3], float radius, int mtype, con
   o.mat = makeMaterial(mtype, rgb, refl, transp, (int)ctx->objs.size());
   o.center[0] = c[0]; o.center[1] = c[1]; o.center[2] = c[2];
   o.sqRadius = radius * radius;                                 // Sphere.cpp:19
+  o.radius = radius;
   ctx->objs.push_back(o);
   ctx->sceneDirty = true;
   return (int)ctx->objs.size() - 1;
@@ -1102,6 +1188,14 @@ int rfx_force_path(rfx_ctx * ctx, int path)
 {
   if (!ctx || path < 0 || path > 2) return RFX_ERR_ARG;
   ctx->forcePath = path;
+  return RFX_OK;
+}
+
+int rfx_set_bvh_mode(rfx_ctx * ctx, int mode)
+{
+  if (!ctx || mode < 0 || mode > 2) return RFX_ERR_ARG;
+  ctx->bvhMode = mode;
+  ctx->sceneDirty = true;
   return RFX_OK;
 }
 

@@ -231,7 +231,8 @@ __device__ __forceinline__ bool intersectAll(const SceneView & sc, V3 o, V3 d, i
   const float a4 = 4.0f * a, a2 = 2.0f * a;          // Sphere.cpp:53,57
   const bool aOk = a > RFX_VSN;
 
-  for (int i = 0; i < h.nSpheres; i++)
+  // exact test of sphere i (reference Sphere.cpp:44-85); returns true when an any-hit query is satisfied
+  auto testSphere = [&](int i) -> bool
   {
     const float4 s = sc.spheres[i];
     const float vx = o.x - s.x, vy = o.y - s.y, vz = o.z - s.z;
@@ -254,6 +255,48 @@ __device__ __forceinline__ bool intersectAll(const SceneView & sc, V3 o, V3 d, i
             best.dist = dist; best.idx = i; best.order = order; best.t = t;
           }
         }
+      }
+    }
+    return false;
+  };
+
+  if (h.bvhNodes == nullptr)
+  {
+    for (int i = 0; i < h.nSpheres; i++)
+      if (testSphere(i)) return true;
+  }
+  else
+  {
+    // Bounding-volume hierarchy over the spheres (SURVEY f-3).  It only decides WHICH spheres get the exact test above;
+    // boxes are inflated by a margin three orders of magnitude above the float error of that test, the slab test is
+    // NaN-tolerant (fminf/fmaxf drop NaNs), and ties still go to the lowest insertion index, so the result is identical
+    // to the reference's list walk (checked against brute force in tests/test_gpu_parity.py::test_bvh_equals_brute_force).
+    const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+    const float lenD = sqrtf(a);
+    int stack[32];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp)
+    {
+      const int ni = stack[--sp];
+      const float4 lo = __ldg(&h.bvhNodes[2 * ni]), hi = __ldg(&h.bvhNodes[2 * ni + 1]);
+      const float tx1 = (lo.x - o.x) * ix, tx2 = (hi.x - o.x) * ix;
+      const float ty1 = (lo.y - o.y) * iy, ty2 = (hi.y - o.y) * iy;
+      const float tz1 = (lo.z - o.z) * iz, tz2 = (hi.z - o.z) * iz;
+      const float tmin = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fmaxf(fminf(tz1, tz2), 0.0f));
+      const float tmax = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fmaxf(tz1, tz2));
+      if (!(tmin <= tmax)) continue;
+      if (!ANYHIT && tmin * lenD > best.dist * 1.001f + 1e-2f) continue;   // cannot beat the current closest hit (generous slack)
+      const int ca = __float_as_int(lo.w), cb = __float_as_int(hi.w);
+      if (cb < 0)
+      {
+        for (int k = 0; k < -cb; k++)
+          if (testSphere(__ldg(&h.bvhPrims[ca + k]))) return true;
+      }
+      else if (sp < 31)
+      {
+        stack[sp++] = ca;
+        stack[sp++] = cb;
       }
     }
   }

@@ -60,6 +60,8 @@ struct SceneHeader
   uint32_t offLights, offSpheres, offTris, offPlanes, offMats, offTex;   // byte offsets inside the blob
   uint32_t bytes;                   // blob size
   const float * byteLut;            // 256 floats: float(i) / 255.0f computed on the host (reference Color.cpp:11-13)
+  const float4 * bvhNodes;          // big scenes: 2 float4 per node {min.xyz, a} {max.xyz, b}; b < 0: leaf of -b prims starting at a; else children a, b
+  const int * bvhPrims;             // sphere indices (sorted-array positions) referenced by the leaves
 };
 
 // Small scenes travel as a kernel parameter (constant bank): see rfx_trace_small.cu

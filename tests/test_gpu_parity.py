@@ -137,3 +137,35 @@ def test_error_behaviour(capi):
         assert np.array_equal(c.read_pixel(-1, 0), np.zeros(3, np.float32))   # Render.cpp:112-113
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("n_side,size,depth", [(6, (128, 72), 8), (12, (160, 90), 6), (32, (96, 54), 4)])
+def test_bvh_equals_brute_force(capi, oracle, n_side, size, depth):
+    """SURVEY f-3: the bounding-volume hierarchy of the shared-memory kernel only selects which spheres get the exact test;
+    the float image, the hit-path signatures and the ray counts must be IDENTICAL to the brute-force list walk, and both
+    must meet the parity bar against the oracle."""
+    W, H = size
+    scene = S.synthetic_scene(n_side, floor=S.synthetic_texture(64, 64, 3), skybox=S.synthetic_texture(128, 96, 5))
+    cams = [S.default_camera(), S.orbit_cameras(7)[3]]
+    out = {}
+    for mode in (2, 1):
+        c = capi.Context(0)
+        try:
+            c.load_scene(scene); c.set_seeds(321, 321); c.set_image_size(W, H)
+            c.force_path(2); c.set_bvh_mode(mode); c.enable_signatures(True); c.stats_reset()
+            frames = []
+            for cam in cams:
+                c.render(cam, depth)
+                frames.append((c.read_rgbf(), c.read_argb(), c.read_signatures()))
+            out[mode] = (frames, c.stats()["rays"], c.get_seeds())
+        finally:
+            c.close()
+    assert out[1][1] == out[2][1] and out[1][2] == out[2][2]
+    for (f1, a1, s1), (f2, a2, s2) in zip(out[1][0], out[2][0]):
+        assert np.array_equal(f1.view(np.uint32), f2.view(np.uint32))
+        assert np.array_equal(s1, s2)
+    o = oracle.OracleRender(scene, W, H, seed=321)
+    for k, cam in enumerate(cams):
+        o.render(cam, depth, want_sig=True)
+        assert np.array_equal(out[1][0][k][2], o.sig)
+        cases.assert_parity(out[1][0][k][1], o.resolve()[1], "bvh frame %d" % k)

@@ -90,3 +90,21 @@ def test_shim_scene_trace_matches_render(rfx_lib):
     frames = run_shim_harness(["--refl", "6", "--rows", "3", "1"], 99, 24, 18)
     rgbf, argb = frames[0]
     assert np.all(argb[0::3] == 0) and np.any(argb[1::3] != 0)
+
+
+def test_shim_texture_file_formats(tmp_path):
+    """f-4: 32-bpp bottom-up BMP and type-2 TGA exactly as the reference writes them (Texture.cpp:110-173, image_headers.h)."""
+    import struct
+    exe = str(tmp_path / "texture_io")
+    subprocess.run(["g++", "-std=c++14", "-O1", "-I" + SHIM, "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "texture_io.cpp"), "-o", exe], check=True)
+    subprocess.run([exe, str(tmp_path)], check=True)
+    px = np.array([(0x01020300 * (i + 1) + i) & 0xFFFFFFFF for i in range(15)], dtype="<u4")
+    bmp = (tmp_path / "a.bmp").read_bytes()
+    bfType, bfSize, _, _, bfOff = struct.unpack_from("<HIHHI", bmp, 0)
+    biSize, w, h, planes, bpp, comp = struct.unpack_from("<IiiHHI", bmp, 14)
+    assert (bfType, bfSize, bfOff, biSize, w, h, planes, bpp, comp) == (0x4D42, 54 + 60, 54, 40, 5, 3, 1, 32, 0)
+    assert bmp[54:] == px.tobytes()
+    tga = (tmp_path / "a.tga").read_bytes()
+    assert struct.unpack_from("<bbbhhbhhhhbb", tga, 0) == (0, 0, 2, 0, 0, 0, 0, 0, 5, 3, 32, 0)
+    assert tga[18:] == px.tobytes()
