@@ -122,6 +122,9 @@ RFX_API int rfx_enable_signatures(rfx_ctx * ctx, int on);
  * NVLink, see rfx_ipc_*): the kernel then stores its pixels straight into the gathering GPU's framebuffer. */
 RFX_API int rfx_render_range(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argb_device, void * stream);
 RFX_API int rfx_render_finish(rfx_ctx * ctx);
+/* the same for the usual partition — interleaved strips of strip_rows rows, strip s owned by rank s % world — in ONE random-stream
+ * pass over the frame and ONE trace launch covering only this rank's rows; completes the frame (no rfx_render_finish needed) */
+RFX_API int rfx_render_strips(rfx_ctx * ctx, uint32_t strip_rows, uint32_t world, uint32_t rank, uint32_t * argb_device, void * stream);
 /* device buffers that can be shared between the per-GPU processes of one node (cudaIpc) */
 RFX_API int rfx_buffer_alloc(rfx_ctx * ctx, uint64_t bytes, void ** device_ptr);
 RFX_API int rfx_buffer_free(rfx_ctx * ctx, void * device_ptr);

@@ -63,6 +63,7 @@ SYMBOLS = [
     ("rfx_trace_rays", C.c_int, [C.c_void_p, C.c_int, _fp, _fp, C.c_int, _fp]),
     ("rfx_render_range", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     ("rfx_render_finish", C.c_int, [C.c_void_p]),
+    ("rfx_render_strips", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     ("rfx_buffer_alloc", C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     ("rfx_buffer_free", C.c_int, [C.c_void_p, C.c_void_p]),
     ("rfx_buffer_read", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -243,6 +244,9 @@ class Context:
     # ---- frame splitting / shared buffers ---------------------------------------------------------------------
     def render_range(self, p0, p1, argb_device_ptr=0, stream=0):
         self._ck(self.L.rfx_render_range(self.h, p0, p1, C.c_void_p(int(argb_device_ptr) or None), C.c_void_p(int(stream) or None)), "rfx_render_range")
+
+    def render_strips(self, strip_rows, world, rank, argb_device_ptr, stream=0):
+        self._ck(self.L.rfx_render_strips(self.h, strip_rows, world, rank, C.c_void_p(int(argb_device_ptr)), C.c_void_p(int(stream) or None)), "rfx_render_strips")
 
     def render_finish(self):
         self._ck(self.L.rfx_render_finish(self.h), "rfx_render_finish")

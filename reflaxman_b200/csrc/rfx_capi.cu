@@ -379,7 +379,7 @@ uint64_t originsBefore(uint64_t p, uint32_t W, uint32_t a)
 }
 
 // rank n Scene::trace calls on the randDir stream; the states land in ctx->dSampleStates (or nowhere when skipOnly)
-int rankSamples(rfx_ctx * ctx, uint64_t n, bool skipOnly, cudaStream_t st)
+int rankSamples(rfx_ctx * ctx, uint64_t n, bool skipOnly, cudaStream_t st, uint64_t ownPeriod = 0, uint32_t ownWorld = 0, uint32_t ownRank = 0)
 {
   if (n == 0) return RFX_OK;
   const uint32_t nBlocks = rngBlocksFor(n);
@@ -398,6 +398,7 @@ int rankSamples(rfx_ctx * ctx, uint64_t n, bool skipOnly, cudaStream_t st)
   w.status = ctx->dStatus;
   w.n = n;
   w.nBlocks = nBlocks;
+  w.ownPeriod = ownPeriod; w.ownWorld = ownWorld; w.ownRank = ownRank;
   ctx->stats.kernel_launches += launchRngRank(w, st);
   CK(cudaGetLastError());
   ctx->rngSlot ^= 1;
@@ -846,6 +847,58 @@ int rfx_render_range(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argb_de
   if (p0 > ctx->cursor && (rc = skipPixels(ctx, ctx->cursor, p0, st)) != RFX_OK) return rc;
   if ((rc = renderRange(ctx, p0, p1, argb_device, argb_device == nullptr, st)) != RFX_OK) return rc;
   ctx->cursor = p1;
+  return RFX_OK;
+}
+
+int rfx_render_strips(rfx_ctx * ctx, uint32_t strip_rows, uint32_t world, uint32_t rank, uint32_t * argb_device, void * stream)
+{
+  if (!ctx || !argb_device || !strip_rows || !world || rank >= world) return fail(ctx, RFX_ERR_ARG, "rfx_render_strips: bad argument");
+  const uint64_t total = (uint64_t)ctx->W * ctx->H;
+  if (!ctx->inProgress || ctx->cursor != 0) return fail(ctx, RFX_ERR_ARG, "rfx_render_strips: needs a freshly begun frame");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  int rc;
+  if ((rc = useStream(ctx, st)) != RFX_OK) return rc;
+  if ((rc = uploadScene(ctx, st)) != RFX_OK) return rc;
+  const uint64_t calls = ctx->sampleNum > 0 ? callsIn(ctx, 0, total) : 0;
+  const bool fast = ctx->sampleNum > 0 && ctx->smallOk && ctx->forcePath != 2 && !ctx->snap.jitter && !ctx->sigOn &&
+                    strip_rows % 8 == 0 && calls <= (1ull << 26);
+  if (!fast)
+  {
+    // general path: one range per strip (block preview, big scenes, huge SSAA factors)
+    const uint32_t nStrips = (ctx->H + strip_rows - 1) / strip_rows;
+    for (uint32_t s = rank; s < nStrips; s += world)
+    {
+      const uint64_t p0 = (uint64_t)s * strip_rows * ctx->W, p1 = std::min<uint64_t>(total, (uint64_t)(s + 1) * strip_rows * ctx->W);
+      if ((rc = rfx_render_range(ctx, p0, p1, argb_device, stream)) != RFX_OK) return rc;
+    }
+    return rfx_render_finish(ctx);
+  }
+  const uint64_t perPixel = (uint64_t)ctx->sampleNum * ctx->sampleNum;
+  // K1 once over the whole frame (every GPU needs the accept counts of everything before its rows); only the states of
+  // this rank's strips are stored
+  if ((rc = rankSamples(ctx, calls, false, st, (uint64_t)strip_rows * ctx->W * perPixel, world, rank)) != RFX_OK) return rc;
+  TraceWork w;
+  w.sceneBlob = ctx->dBlob; w.sceneBytes = ctx->blobBytes;
+  w.fp = ctx->snap;
+  w.fp.p0 = 0; w.fp.p1 = total; w.fp.firstRank = 0; w.fp.seedRender = ctx->seedRender;
+  w.fp.stripRows = strip_rows; w.fp.stripWorld = world; w.fp.stripRank = rank;
+  w.sampleStates = ctx->dSampleStates;
+  w.image = nullptr; w.argbOut = argb_device; w.sigOut = nullptr; w.counters = ctx->dCounters;
+  cudaEvent_t evA = nullptr, evB = nullptr;
+  if (ctx->profiling)
+  {
+    if (ctx->evUsed + 2 > ctx->evPool.size())
+      for (int i = 0; i < 2; i++) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->evPool.push_back(e); }
+    evA = ctx->evPool[ctx->evUsed++]; evB = ctx->evPool[ctx->evUsed++];
+    CK(cudaEventRecord(evA, st));
+  }
+  ctx->stats.kernel_launches += launchTraceSmall(ctx->small, w, st);
+  if (evB) CK(cudaEventRecord(evB, st));
+  CK(cudaGetLastError());
+  ctx->stats.samples += calls / world;
+  ctx->cursor = total;
+  ctx->inProgress = false;
   return RFX_OK;
 }
 

@@ -108,11 +108,22 @@ __global__ void __launch_bounds__(1024) k_rng_scan(const uint32_t * __restrict__
 
 __global__ void __launch_bounds__(RNG_THREADS) k_rng_scatter(const uint32_t * __restrict__ stateIn, uint32_t * __restrict__ stateOut,
                                                              const uint32_t * __restrict__ blockOffsets, const uint8_t * __restrict__ acceptMasks,
-                                                             uint32_t * __restrict__ sampleStates, unsigned long long n, uint32_t rankBase)
+                                                             uint32_t * __restrict__ sampleStates, unsigned long long n, uint32_t rankBase,
+                                                             unsigned long long ownPeriod, uint32_t ownWorld, uint32_t ownRank)
 {
   __shared__ int warpSums[RNG_THREADS / 32];
   const unsigned long long boff = (unsigned long long)blockOffsets[blockIdx.x] + rankBase;
   if (boff >= n) return;   // uniform per CTA
+  // skip-only pass (rfx_skip_samples): nothing to store, only the CTA that can hold rank n-1 has work (the stream-end state)
+  if (!sampleStates && boff + RNG_TRIPLES_PER_BLOCK - 1 < n - 1) return;
+  if (ownWorld)
+  {
+    // split frames: a CTA whose whole rank range lies in one strip of another GPU has nothing to store (the stream-end
+    // state is written by whoever holds rank n-1, so the CTA that may contain it is never skipped)
+    const unsigned long long last = boff + RNG_TRIPLES_PER_BLOCK - 1;   // upper bound of the ranks this CTA can hold
+    const unsigned long long s0 = boff / ownPeriod, s1 = last / ownPeriod;
+    if (s0 == s1 && (uint32_t)(s0 % ownWorld) != ownRank && last < n - 1) return;
+  }
 
   const uint32_t gid = blockIdx.x * RNG_THREADS + threadIdx.x;
   const uint32_t sStart = lcgJump(*stateIn, gid * (3u * RNG_TRIPLES_PER_THREAD));
@@ -145,7 +156,7 @@ __global__ void __launch_bounds__(RNG_THREADS) k_rng_scatter(const uint32_t * __
     {
       if (rank < n)
       {
-        if (sampleStates) sampleStates[rank] = before;
+        if (sampleStates && (!ownWorld || (uint32_t)((rank / ownPeriod) % ownWorld) == ownRank)) sampleStates[rank] = before;
         if (rank == n - 1) *stateOut = s;
       }
       rank++;
@@ -164,7 +175,8 @@ int launchRngRank(const RngWork & w, cudaStream_t st)
 {
   k_rng_count<<<w.nBlocks, RNG_THREADS, 0, st>>>(w.stateIn, w.blockCounts, w.acceptMasks);
   k_rng_scan<<<1, 1024, 0, st>>>(w.blockCounts, w.blockOffsets, w.nBlocks, (unsigned long long)w.n, w.status);
-  k_rng_scatter<<<w.nBlocks, RNG_THREADS, 0, st>>>(w.stateIn, w.stateOut, w.blockOffsets, w.acceptMasks, w.sampleStates, (unsigned long long)w.n, 0u);
+  k_rng_scatter<<<w.nBlocks, RNG_THREADS, 0, st>>>(w.stateIn, w.stateOut, w.blockOffsets, w.acceptMasks, w.sampleStates, (unsigned long long)w.n, 0u,
+                                                      (unsigned long long)w.ownPeriod, w.ownWorld, w.ownRank);
   return 3;
 }
 

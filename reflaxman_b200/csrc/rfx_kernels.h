@@ -27,6 +27,9 @@ struct RngWork
   int * status;                 // device: set to 1 when fewer than n triples were accepted in nBlocks blocks
   uint64_t n;                   // accepted triples wanted
   uint32_t nBlocks;
+  // optional scatter filter (split frames): only ranks r with (r / ownPeriod) % ownWorld == ownRank are stored (ownWorld = 0: all)
+  uint64_t ownPeriod = 0;
+  uint32_t ownWorld = 0, ownRank = 0;
 };
 // number of blocks that over-provisions n accepted triples (acceptance pi/6 = 0.5236)
 uint32_t rngBlocksFor(uint64_t n);

@@ -394,6 +394,12 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
     const uint32_t warp = (uint32_t)(gid >> 5), lane = threadIdx.x & 31u;
     x = (warp % tilesX) * RFX_TILE_W + (lane % RFX_TILE_W);
     y = y0 + (warp / tilesX) * RFX_TILE_H + (lane / RFX_TILE_W);
+    if (fp.stripWorld)
+    {
+      // split frame: the launch enumerates only this GPU's rows; compact row -> (own strip k, row in strip) -> frame row
+      const uint32_t k = y / fp.stripRows;
+      y = (k * fp.stripWorld + fp.stripRank) * fp.stripRows + (y % fp.stripRows);
+    }
     valid = x < fp.W && y < y1;
     firstState = (((uint64_t)y * fp.W + x) - fp.p0) * (uint64_t)(sn * sn);
   }
@@ -490,7 +496,14 @@ int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st
     if (fp.p0 % fp.W == 0 && fp.p1 % fp.W == 0)
     {
       tiled = 1;
-      const uint64_t rows = (fp.p1 - fp.p0) / fp.W;
+      uint64_t rows = (fp.p1 - fp.p0) / fp.W;
+      if (fp.stripWorld)
+      {
+        // rows owned by this rank: full strips plus the (possibly shorter) last strip, rounded up to whole strips
+        const uint64_t nStrips = (rows + fp.stripRows - 1) / fp.stripRows;
+        const uint64_t mine = nStrips > fp.stripRank ? (nStrips - fp.stripRank + fp.stripWorld - 1) / fp.stripWorld : 0;
+        rows = mine * fp.stripRows;
+      }
       nThreads = (uint64_t)((fp.W + RFX_TILE_W - 1) / RFX_TILE_W) * ((rows + RFX_TILE_H - 1) / RFX_TILE_H) * 32;
     }
     else

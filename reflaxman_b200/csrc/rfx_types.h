@@ -102,6 +102,7 @@ struct FrameParams                  // one renderBegin snapshot + the renderNext
   uint32_t seedRender;              // Render.cpp TU LCG state at the first pixel of this slice
   uint64_t p0, p1;                  // linear pixel range [p0, p1) of this slice, scan order (y-major)
   uint64_t firstRank;               // block-preview mode: number of block origins before p0
+  uint32_t stripRows, stripWorld, stripRank;   // split-frame mode (stripWorld > 0): this launch owns strips s with s % stripWorld == stripRank
 };
 
 struct Counters                     // device-side event counters (uint64 each)

@@ -58,6 +58,13 @@ def split_frame(ctx, cam, refl, samples, world, rank, gather_ptr, strip_rows=16,
     be peer memory on the gathering GPU).  Leaves the random stream where a full-frame render would."""
     ctx.set_camera(cam)
     ctx.render_begin(refl, samples, False)
+    ctx.render_strips(strip_rows, world, rank, gather_ptr, stream)   # one K1 pass + one K2 launch over this rank's rows
+
+
+def split_frame_by_ranges(ctx, cam, refl, samples, world, rank, gather_ptr, strip_rows=16, stream=0):
+    """The same through the general range API (one launch per strip) — kept as the cross-check of render_strips."""
+    ctx.set_camera(cam)
+    ctx.render_begin(refl, samples, False)
     for p0, p1 in strip_ranges(ctx.W, ctx.H, world, rank, strip_rows):
         ctx.render_range(p0, p1, gather_ptr, stream)
     ctx.render_finish()

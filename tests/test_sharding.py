@@ -100,11 +100,12 @@ def test_gpu_frame_sharding_matches_sequence(rfx_lib, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("by_ranges", [False, True], ids=["strips", "ranges"])
 @pytest.mark.parametrize("samples", [1, 2, -3])
-def test_gpu_split_frame_equals_whole_frame(rfx_lib, samples):
+def test_gpu_split_frame_equals_whole_frame(rfx_lib, samples, by_ranges):
     """two 'ranks' (contexts) render interleaved strips of one frame straight into one shared buffer"""
     from reflaxman_b200 import capi
-    w, h = 64, 50
+    w, h = 64, 52
     cam = S.default_camera()
     whole = capi.Context(0)
     whole.load_scene(S.default_scene()); whole.set_seeds(5, 5); whole.set_image_size(w, h)
@@ -112,11 +113,11 @@ def test_gpu_split_frame_equals_whole_frame(rfx_lib, samples):
     want = whole.read_argb()
     seeds_after = whole.get_seeds()
     gather = whole.buffer_alloc(w * h * 4)
-    world = 2
+    world = 3
     for rank in range(world):
         d = capi.Context(0)
         d.load_scene(S.default_scene()); d.set_seeds(5, 5); d.set_image_size(w, h)
-        P.split_frame(d, cam, REFL, samples, world, rank, gather, strip_rows=6 if samples > 0 else 6)
+        (P.split_frame_by_ranges if by_ranges else P.split_frame)(d, cam, REFL, samples, world, rank, gather, strip_rows=6 if by_ranges else 8)
         d.synchronize()
         assert d.get_seeds() == seeds_after          # the stream ends where the unsplit render ends
         d.close()
