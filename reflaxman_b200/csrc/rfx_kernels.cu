@@ -473,7 +473,7 @@ __device__ V3 traceSample(const SceneView & sc, V3 origin, V3 ray, int reflNumbe
               {
                 if (L.radius > RFX_VSN)
                 {
-                  const float sp = powf(rsc, 1 + 3 * m.reflectivity * toLightLen / L.radius) * m.reflectivity;   // Scene.cpp:175
+                  const float sp = powLikePowf(rsc, 1 + 3 * m.reflectivity * toLightLen / L.radius) * m.reflectivity;   // Scene.cpp:175
                   sumSpec.x = sumSpec.x + L.r * sp;
                   sumSpec.y = sumSpec.y + L.g * sp;
                   sumSpec.z = sumSpec.z + L.b * sp;
@@ -492,7 +492,7 @@ __device__ V3 traceSample(const SceneView & sc, V3 origin, V3 ray, int reflNumbe
       {
         const float a = rayLen * normLen;
         const float cosA = (a > RFX_VSN) ? clamp01(((ray.x * -norm.x + ray.y * -norm.y) + ray.z * -norm.z) / a) : 0.0f;
-        const float rf = 0.2f + 0.8f * powf(1.0f - cosA, 3.0f);
+        const float rf = 0.2f + 0.8f * cubeLikePowf(1.0f - cosA);
         const float k = 1.0f - rf;
         fin = mk(((color.x * k) * sumLight.x + sumSpec.x) * mul.x, ((color.y * k) * sumLight.y + sumSpec.y) * mul.y,
                  ((color.z * k) * sumLight.z + sumSpec.z) * mul.z);

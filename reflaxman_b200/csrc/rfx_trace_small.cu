@@ -51,7 +51,6 @@ struct Best
   float ax, ay, az;  // sphere centre, or triangle/plane normal — whatever the hit record needs from the object
 };
 
-static __device__ __noinline__ float powfShared(float x, float y) { return powf(x, y); }
 
 // ---- reject tests -------------------------------------------------------------------------------------------------
 // sphere i: discriminant of Sphere.cpp:49-53 with the per-ray invariants hoisted; sets bit i when d >= 0
@@ -322,7 +321,7 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
             rsc = clamp01(rsc + (1.0f - sqrtf(larsc)));
             if (rsc > RFX_VSN && L.radius > RFX_VSN)
             {
-              const float sp = powfShared(rsc, 1 + 3 * m.reflectivity * toLightLen / L.radius) * m.reflectivity;   // Scene.cpp:175
+              const float sp = powLikePowf(rsc, 1 + 3 * m.reflectivity * toLightLen / L.radius) * m.reflectivity;   // Scene.cpp:175
               sumSpec.x = sumSpec.x + L.r * sp;
               sumSpec.y = sumSpec.y + L.g * sp;
               sumSpec.z = sumSpec.z + L.b * sp;
@@ -340,7 +339,7 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
     {
       const float a = rayLen * normLen;
       const float cosA = (a > RFX_VSN) ? clamp01(((ray.x * -norm.x + ray.y * -norm.y) + ray.z * -norm.z) / a) : 0.0f;
-      rf = 0.2f + 0.8f * powfShared(1.0f - cosA, 3.0f);
+      rf = 0.2f + 0.8f * cubeLikePowf(1.0f - cosA);
     }
     const float k = 1.0f - rf;
     const V3 fin = mk(((color.x * k) * sumLight.x + sumSpec.x) * mul.x, ((color.y * k) * sumLight.y + sumSpec.y) * mul.y,
