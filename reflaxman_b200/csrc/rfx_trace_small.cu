@@ -3,13 +3,15 @@
 //
 // Design (B200, FP32 CUDA cores; this path has no dense contraction, so no tensor cores):
 //   * The whole scene travels as a __grid_constant__ kernel parameter: every sphere/triangle coefficient is a
-//     constant-bank operand of the FADD/FMUL that uses it — no loads, no address arithmetic in the test loops.
-//   * The reject tests (sphere discriminant, triangle plane-side) are straight-line, fully unrolled and branch-free;
-//     they only set a per-lane candidate bit.  The rare candidates are then resolved one object at a time for the
-//     whole warp (warp-uniform object index), so the expensive sqrt/divide path is entered once per distinct
-//     candidate object per warp instead of once per loop iteration per lane.
-//   * The same routine answers closest-hit and shadow (any-hit) queries.
-//   * Warps own 4x8 pixel tiles of row-aligned slices (coherent primary/secondary rays; 8x4, 16x2, 32x1 measured slower).
+//     constant-bank operand — no global loads, no address arithmetic in the test loops.
+//   * ONE intersection call site.  Scene::trace is a state machine per lane: the query in flight is either the bounce
+//     segment (closest hit) or the shadow ray of light `li` (any hit); lanes in either state share the same pass over
+//     the objects.  That halves the code of the kernel (the instruction working set now fits the 32 KB L1.5
+//     instruction cache) and keeps lanes of a warp that sit in different phases busy in the same loop.
+//   * The pass over the objects is one rolled loop per kind: the branch-free reject test (sphere discriminant and ray
+//     side, triangle plane side) followed, for the lanes that pass it, by the sqrt/divide tail.
+//   * Warps own 4x8 pixel tiles (coherent primary/secondary rays; 8x4, 16x2, 32x1 measured slower); the fast kernel
+//     (whole rows, 1 sample per pixel, ARGB only) uses a 2-D grid so that no thread executes an integer division.
 //   * The bounce recursion is the reference's own bounded iterative loop carrying throughput (mulColor).
 //
 // ARITHMETIC CONTRACT: compiled with --fmad=false, no fast-math: every + - * / sqrtf is the IEEE binary32 RN
@@ -24,9 +26,6 @@
 namespace rfx
 {
 
-#ifndef RFX_SMALL_UNROLL
-#define RFX_SMALL_UNROLL 0
-#endif
 #ifndef RFX_TILE_W
 #define RFX_TILE_W 4u      // pixel tile of one warp: RFX_TILE_W x RFX_TILE_H = 32 (4x8 measured best, profiles/variants_d_r1.jsonl)
 #endif
@@ -38,321 +37,277 @@ namespace rfx
 #define RFX_SMALL_MINBLOCKS 3
 #endif
 
-constexpr int SM_TRI_BIT = SMALL_MAX_SPHERES;                       // candidate-mask bit layout: spheres | triangles | planes
+constexpr int SM_TRI_BIT = SMALL_MAX_SPHERES;                       // object slots: spheres | triangles | planes
 constexpr int SM_PLANE_BIT = SMALL_MAX_SPHERES + SMALL_MAX_TRIS;
 
 struct Best
 {
   float dist;
-  int slot;          // candidate-mask bit of the winning object, -1 = none
+  int slot;          // slot of the winning object, -1 = none
   int order;         // insertion index (closest-hit tie-break, reference Scene.cpp:98 walks the list in order)
   float t;
   float u, v;        // triangle barycentrics
-  float ax, ay, az;  // sphere centre, or triangle/plane normal — whatever the hit record needs from the object
 };
 
-
-// ---- reject tests -------------------------------------------------------------------------------------------------
-// sphere i: discriminant of Sphere.cpp:49-53 with the per-ray invariants hoisted; sets bit i when d >= 0
-#define RFX_SPHERE_REJECT(i)                                                         \
-  {                                                                                  \
-    const float vx = o.x - sc.sph[i].x, vy = o.y - sc.sph[i].y, vz = o.z - sc.sph[i].z; \
-    const float b = (r2x * vx + r2y * vy) + r2z * vz;                                \
-    const float c = ((vx * vx + vy * vy) + vz * vz) - sc.sph[i].w;                   \
-    const float disc = b * b - a4 * c;                                               \
-    if (disc >= 0.0f) mask |= 1u << (i);                                             \
-  }
-
-// triangle k: third row of axTrans*(origin - v0) and axTrans*ray (Triangle.cpp:56-57, Matrix33.cpp:232-234);
-// t = -oz/rz > 2^-63 needs |rz| > 2^-63 and oz, rz of strictly opposite sign (the sign of an IEEE quotient is exact),
-// so everything else is skipped without dividing
-#define RFX_TRI_REJECT(k)                                                            \
-  {                                                                                  \
-    const float px = o.x - sc.tri[k].v0[0], py = o.y - sc.tri[k].v0[1], pz = o.z - sc.tri[k].v0[2]; \
-    const float oz = (px * sc.tri[k].ax[6] + py * sc.tri[k].ax[7]) + pz * sc.tri[k].ax[8]; \
-    const float rz = (d.x * sc.tri[k].ax[6] + d.y * sc.tri[k].ax[7]) + d.z * sc.tri[k].ax[8]; \
-    if (fabsf(rz) > RFX_VSN && ((oz < 0.0f && rz > 0.0f) || (oz > 0.0f && rz < 0.0f))) mask |= 1u << (SM_TRI_BIT + (k)); \
-  }
-
-__device__ __forceinline__ void considerHit(Best & best, float dist, int slot, int order, float t, float u, float v, float ax, float ay, float az)
+__device__ __forceinline__ void considerHit(Best & best, float dist, int slot, int order, float t, float u, float v)
 {
   if (dist < best.dist || (dist == best.dist && order < best.order))
   {
     best.dist = dist; best.slot = slot; best.order = order; best.t = t; best.u = u; best.v = v;
-    best.ax = ax; best.ay = ay; best.az = az;
   }
 }
 
-// all objects against one ray; objects whose bit is set in skipMask are ignored (the shadow loop's `*obj != hitObject`)
-__device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d, uint32_t skipMask, Best & best)
+// All objects against one ray.  `skip` is the slot the query ignores (the shadow loop's `*obj != hitObject`,
+// Scene.cpp:135; -1 = none).  anyHit: the caller only asks whether something is hit (shadow query), so a lane that has
+// found an occluder stops entering the sqrt/divide tails.
+__device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d, int skip, bool anyHit, Best & best)
 {
   const float a = vsqlen(d);                                          // Sphere.cpp:50
   const float r2x = d.x * 2.0f, r2y = d.y * 2.0f, r2z = d.z * 2.0f;   // 2.0f * ray, Sphere.cpp:51
   const float a4 = 4.0f * a, a2 = 2.0f * a;                           // Sphere.cpp:53,57
-  uint32_t mask = 0;
+  const bool aOk = a > RFX_VSN;                                       // Sphere.cpp:55 `a > VERY_SMALL_NUMBER`
 
-#if RFX_SMALL_UNROLL == 2
-  // experiment: counts fixed at compile time -> straight-line code, immediate constant-bank offsets, no indirect branch
-#pragma unroll
-  for (int i = 0; i < RFX_FIX_NS; i++) RFX_SPHERE_REJECT(i)
-  if (!(a > RFX_VSN)) mask = 0;
-#pragma unroll
-  for (int k = 0; k < RFX_FIX_NT; k++) RFX_TRI_REJECT(k)
-#elif RFX_SMALL_UNROLL
-  switch (sc.nS)   // fall-through: straight-line code for exactly nS spheres
-  {
-  case 16: RFX_SPHERE_REJECT(15)
-  case 15: RFX_SPHERE_REJECT(14)
-  case 14: RFX_SPHERE_REJECT(13)
-  case 13: RFX_SPHERE_REJECT(12)
-  case 12: RFX_SPHERE_REJECT(11)
-  case 11: RFX_SPHERE_REJECT(10)
-  case 10: RFX_SPHERE_REJECT(9)
-  case 9: RFX_SPHERE_REJECT(8)
-  case 8: RFX_SPHERE_REJECT(7)
-  case 7: RFX_SPHERE_REJECT(6)
-  case 6: RFX_SPHERE_REJECT(5)
-  case 5: RFX_SPHERE_REJECT(4)
-  case 4: RFX_SPHERE_REJECT(3)
-  case 3: RFX_SPHERE_REJECT(2)
-  case 2: RFX_SPHERE_REJECT(1)
-  case 1: RFX_SPHERE_REJECT(0)
-  default: break;
-  }
-  if (!(a > RFX_VSN)) mask = 0;                                       // Sphere.cpp:55 `a > VERY_SMALL_NUMBER`
-
-  switch (sc.nT)
-  {
-  case 8: RFX_TRI_REJECT(7)
-  case 7: RFX_TRI_REJECT(6)
-  case 6: RFX_TRI_REJECT(5)
-  case 5: RFX_TRI_REJECT(4)
-  case 4: RFX_TRI_REJECT(3)
-  case 3: RFX_TRI_REJECT(2)
-  case 2: RFX_TRI_REJECT(1)
-  case 1: RFX_TRI_REJECT(0)
-  default: break;
-  }
-#else
-  // rolled: a ~20-instruction body that stays resident in the L0 instruction cache; the loop index is warp-uniform,
-  // so sc.sph[i] is a uniform constant-bank load feeding uniform-register operands
-  {
-    uint32_t bit = 1u;
-    const uint32_t endBit = 1u << sc.nS;
+  // ---- spheres: discriminant of Sphere.cpp:49-53 with the per-ray invariants hoisted.  t = (-b - sqrt(disc)) / 2a can
+  // only exceed 2^-63 when b < 0 (sqrt >= 0, 2a > 0), so lanes with b >= 0 never enter the tail — same decisions, fewer sqrt
+  const int nS = sc.nS;
 #pragma unroll 1
-    for (int i = 0; bit != endBit; i++, bit += bit)
-    {
-      const float vx = o.x - sc.sph[i].x, vy = o.y - sc.sph[i].y, vz = o.z - sc.sph[i].z;
-      const float b = (r2x * vx + r2y * vy) + r2z * vz;
-      const float c = ((vx * vx + vy * vy) + vz * vz) - sc.sph[i].w;
-      const float disc = b * b - a4 * c;
-      if (disc >= 0.0f) mask |= bit;
-    }
-    if (!(a > RFX_VSN)) mask = 0;                                     // Sphere.cpp:55 `a > VERY_SMALL_NUMBER`
-    bit = 1u << SM_TRI_BIT;
-    const uint32_t endTri = bit << sc.nT;
-#pragma unroll 1
-    for (int k = 0; bit != endTri; k++, bit += bit)
-    {
-      const float px = o.x - sc.tri[k].v0[0], py = o.y - sc.tri[k].v0[1], pz = o.z - sc.tri[k].v0[2];
-      const float oz = (px * sc.tri[k].ax[6] + py * sc.tri[k].ax[7]) + pz * sc.tri[k].ax[8];
-      const float rz = (d.x * sc.tri[k].ax[6] + d.y * sc.tri[k].ax[7]) + d.z * sc.tri[k].ax[8];
-      if (fabsf(rz) > RFX_VSN && ((oz < 0.0f && rz > 0.0f) || (oz > 0.0f && rz < 0.0f))) mask |= bit;
-    }
-  }
-#endif
-  for (int k = 0; k < sc.nP; k++) mask |= 1u << (SM_PLANE_BIT + k);   // planes are unreachable through the reference's Scene: no reject stage
-  mask &= ~skipMask;
-
-  // resolve candidates, one object at a time for every lane that flagged it
-  uint32_t todo = __reduce_or_sync(__activemask(), mask);
-  while (todo)
+  for (int i = 0; i < nS; i++)
   {
-    const int i = __ffs(todo) - 1;
-    todo &= todo - 1;
-    if ((mask >> i) & 1u)
+    const float4 s = sc.sph[i];
+    const float vx = o.x - s.x, vy = o.y - s.y, vz = o.z - s.z;
+    const float b = (r2x * vx + r2y * vy) + r2z * vz;
+    const float c = ((vx * vx + vy * vy) + vz * vz) - s.w;
+    const float disc = b * b - a4 * c;
+    if (disc >= 0.0f && b < 0.0f && aOk && i != skip && !(anyHit && best.slot >= 0))
     {
-      if (i < SM_TRI_BIT)
+      const float t = (-b - sqrtf(disc)) / a2;                        // Sphere.cpp:57
+      if (t > RFX_VSN)
       {
-        const float4 s = sc.sph[i];
-        const float vx = o.x - s.x, vy = o.y - s.y, vz = o.z - s.z;
-        const float b = (r2x * vx + r2y * vy) + r2z * vz;
-        const float c = ((vx * vx + vy * vy) + vz * vz) - s.w;
-        const float disc = b * b - a4 * c;
-        const float t = (-b - sqrtf(disc)) / a2;                      // Sphere.cpp:57
-        if (t > RFX_VSN)
+        const float fx = d.x * t, fy = d.y * t, fz = d.z * t;
+        const float dist = sqrtf((fx * fx + fy * fy) + fz * fz);      // fullRay.length(), Sphere.cpp:62
+        if (dist > RFX_DELTA) considerHit(best, dist, i, sc.mat[i].order, t, 0.0f, 0.0f);
+      }
+    }
+  }
+
+  // ---- triangles: third row of axTrans*(origin - v0) and axTrans*ray (Triangle.cpp:56-57, Matrix33.cpp:232-234);
+  // t = -oz/rz > 2^-63 needs |rz| > 2^-63 and oz, rz of strictly opposite sign (the sign of an IEEE quotient is exact),
+  // so everything else is skipped without dividing
+  const int nT = sc.nT;
+#pragma unroll 1
+  for (int k = 0; k < nT; k++)
+  {
+    const Triangle & tr = sc.tri[k];
+    const float px = o.x - tr.v0[0], py = o.y - tr.v0[1], pz = o.z - tr.v0[2];
+    const float oz = (px * tr.ax[6] + py * tr.ax[7]) + pz * tr.ax[8];
+    const float rz = (d.x * tr.ax[6] + d.y * tr.ax[7]) + d.z * tr.ax[8];
+    if (fabsf(rz) > RFX_VSN && ((oz < 0.0f && rz > 0.0f) || (oz > 0.0f && rz < 0.0f)) && (SM_TRI_BIT + k) != skip &&
+        !(anyHit && best.slot >= 0))
+    {
+      const float t = -oz / rz;                                       // Triangle.cpp:61
+      if (t > RFX_VSN)
+      {
+        const float ox = (px * tr.ax[0] + py * tr.ax[1]) + pz * tr.ax[2];
+        const float rx = (d.x * tr.ax[0] + d.y * tr.ax[1]) + d.z * tr.ax[2];
+        const float oy = (px * tr.ax[3] + py * tr.ax[4]) + pz * tr.ax[5];
+        const float ry = (d.x * tr.ax[3] + d.y * tr.ax[4]) + d.z * tr.ax[5];
+        const float u = ox + t * rx;                                  // Triangle.cpp:65-66
+        const float v = oy + t * ry;
+        if (u >= 0.0f && v >= 0.0f && u + v < 1.0f)
         {
           const float fx = d.x * t, fy = d.y * t, fz = d.z * t;
-          const float dist = sqrtf((fx * fx + fy * fy) + fz * fz);    // fullRay.length(), Sphere.cpp:62
-          if (dist > RFX_DELTA) considerHit(best, dist, i, sc.mat[i].order, t, 0.0f, 0.0f, s.x, s.y, s.z);
+          const float sq = (fx * fx + fy * fy) + fz * fz;
+          if (sq > RFX_DELTA * RFX_DELTA)
+            considerHit(best, sqrtf(sq), SM_TRI_BIT + k, sc.mat[SM_TRI_BIT + k].order, t, u, v);
         }
       }
-      else if (i < SM_PLANE_BIT)
+    }
+  }
+
+  // ---- planes (unreachable through the reference's Scene, kept for API completeness): Plane.cpp:36-73
+  const int nP = sc.nP;
+#pragma unroll 1
+  for (int k = 0; k < nP; k++)
+  {
+    if ((SM_PLANE_BIT + k) == skip) continue;
+    const Plane & pl = sc.pl[k];
+    const V3 n = mk(pl.n[0], pl.n[1], pl.n[2]);
+    const V3 vop = mk(pl.pos[0] - o.x, pl.pos[1] - o.y, pl.pos[2] - o.z);
+    const float den = vdot(n, d);
+    if (fabsf(den) > RFX_VSN)
+    {
+      const float t = vdot(n, vop) / den;
+      if (t > RFX_VSN)
       {
-        const Triangle & tr = sc.tri[i - SM_TRI_BIT];
-        const float px = o.x - tr.v0[0], py = o.y - tr.v0[1], pz = o.z - tr.v0[2];
-        const float oz = (px * tr.ax[6] + py * tr.ax[7]) + pz * tr.ax[8];
-        const float rz = (d.x * tr.ax[6] + d.y * tr.ax[7]) + d.z * tr.ax[8];
-        const float t = -oz / rz;                                     // Triangle.cpp:61
-        if (t > RFX_VSN)
-        {
-          const float ox = (px * tr.ax[0] + py * tr.ax[1]) + pz * tr.ax[2];
-          const float rx = (d.x * tr.ax[0] + d.y * tr.ax[1]) + d.z * tr.ax[2];
-          const float oy = (px * tr.ax[3] + py * tr.ax[4]) + pz * tr.ax[5];
-          const float ry = (d.x * tr.ax[3] + d.y * tr.ax[4]) + d.z * tr.ax[5];
-          const float u = ox + t * rx;                                // Triangle.cpp:65-66
-          const float v = oy + t * ry;
-          if (u >= 0.0f && v >= 0.0f && u + v < 1.0f)
-          {
-            const float fx = d.x * t, fy = d.y * t, fz = d.z * t;
-            const float sq = (fx * fx + fy * fy) + fz * fz;
-            if (sq > RFX_DELTA * RFX_DELTA)
-              considerHit(best, sqrtf(sq), i, sc.mat[i].order, t, u, v, tr.n[0], tr.n[1], tr.n[2]);
-          }
-        }
-      }
-      else
-      {
-        const Plane & pl = sc.pl[i - SM_PLANE_BIT];                   // Plane.cpp:36-73
-        const V3 n = mk(pl.n[0], pl.n[1], pl.n[2]);
-        const V3 vop = mk(pl.pos[0] - o.x, pl.pos[1] - o.y, pl.pos[2] - o.z);
-        const float den = vdot(n, d);
-        if (fabsf(den) > RFX_VSN)
-        {
-          const float t = vdot(n, vop) / den;
-          if (t > RFX_VSN)
-          {
-            const float fx = d.x * t, fy = d.y * t, fz = d.z * t;
-            const float sq = (fx * fx + fy * fy) + fz * fz;
-            if (sq > RFX_DELTA * RFX_DELTA) considerHit(best, sqrtf(sq), i, sc.mat[i].order, t, 0.0f, 0.0f, n.x, n.y, n.z);
-          }
-        }
+        const float fx = d.x * t, fy = d.y * t, fz = d.z * t;
+        const float sq = (fx * fx + fy * fy) + fz * fz;
+        if (sq > RFX_DELTA * RFX_DELTA) considerHit(best, sqrtf(sq), SM_PLANE_BIT + k, sc.mat[SM_PLANE_BIT + k].order, t, 0.0f, 0.0f);
       }
     }
   }
 }
 
 // ---- Scene::trace (reference Scene.cpp:73-236) ------------------------------------------------------------------------
+template <bool SIG>
 __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ray, int reflNumber, V3 randDir,
                                          uint32_t & nBounces, uint32_t & nShadow, uint32_t & sig)
 {
   V3 mul = mk(1.0f, 1.0f, 1.0f);
   V3 pix = mk(0.0f, 0.0f, 0.0f);
+  if (reflNumber <= 0) return pix;
 
-  for (int refl = 0; refl < reflNumber; ++refl)
+  // the query in flight: (qo, qd), ignoring slot `skip`; shadowQuery says which of the two states the lane is in
+  V3 qo = origin, qd = ray;
+  int skip = -1;
+  bool shadowQuery = false;
+  int refl = 0, li = 0, hslot = -1;
+  // state of the hit being shaded, alive across its shadow queries
+  V3 drop = origin, norm = ray, reflect = ray, color = mul, sumLight = pix, sumSpec = pix, toLight = ray;
+  float facing = 0.0f, normLen = 0.0f, reflectLen = 0.0f, mrefl = 0.0f;
+  int mtype = 0;
+
+  for (;;)
   {
     Best hit;
-    hit.dist = FLT_MAX; hit.slot = -1; hit.order = 0x7FFFFFFF; hit.t = 0; hit.u = 0; hit.v = 0; hit.ax = hit.ay = hit.az = 0;
-    nBounces++;
-    intersectSmall(sc, origin, ray, 0u, hit);
+    hit.dist = FLT_MAX; hit.slot = -1; hit.order = 0x7FFFFFFF; hit.t = 0; hit.u = 0; hit.v = 0;
+    intersectSmall(sc, qo, qd, skip, shadowQuery, hit);
 
-    if (hit.slot < 0)
+    if (!shadowQuery)
     {
-      RFX_SIG(sig, 0xFFFF);
-      float u, v;
-      skyDirToUv(ray, sc.halfTileW, sc.halfTileH, u, v);
-      const V3 sky = texSampleRef(sc.skyTex >= 0 ? &sc.tex[sc.skyTex] : nullptr, sc.byteLut, u, v);
-      pix = mk(clamp01(pix.x + (mul.x * sky.x) * sc.env[0]), clamp01(pix.y + (mul.y * sky.y) * sc.env[1]),
-               clamp01(pix.z + (mul.z * sky.z) * sc.env[2]));            // Scene.cpp:230-231
-      break;
-    }
-
-    RFX_SIG(sig, hit.order + 1);
-    const V3 full = vscale(ray, hit.t);
-    const V3 drop = vadd(origin, full);
-    const Material m = sc.mat[hit.slot];
-    V3 norm, color = mk(m.r, m.g, m.b);
-    if (hit.slot < SM_TRI_BIT)
-      norm = mk(drop.x - hit.ax, drop.y - hit.ay, drop.z - hit.az);      // Sphere.cpp:67
-    else
-    {
-      norm = mk(hit.ax, hit.ay, hit.az);
-      if (m.tex >= 0)
+      // ---- closest hit of the bounce segment (origin = qo, ray = qd), Scene.cpp:80-112
+      nBounces++;
+      if (hit.slot < 0)
+      {
+        if (SIG) RFX_SIG(sig, 0xFFFF);
+        float u, v;
+        skyDirToUv(ray, sc.halfTileW, sc.halfTileH, u, v);
+        const V3 sky = texSampleRef(sc.skyTex >= 0 ? &sc.tex[sc.skyTex] : nullptr, sc.byteLut, u, v);
+        pix = mk(clamp01(pix.x + (mul.x * sky.x) * sc.env[0]), clamp01(pix.y + (mul.y * sky.y) * sc.env[1]),
+                 clamp01(pix.z + (mul.z * sky.z) * sc.env[2]));            // Scene.cpp:230-231
+        break;
+      }
+      if (SIG) RFX_SIG(sig, hit.order + 1);
+      const V3 full = vscale(ray, hit.t);
+      drop = vadd(qo, full);
+      const Material & m = sc.mat[hit.slot];
+      color = mk(m.r, m.g, m.b);
+      mrefl = m.reflectivity;
+      mtype = m.type;
+      hslot = hit.slot;
+      if (hit.slot < SM_TRI_BIT)
+      {
+        const float4 s = sc.sph[hit.slot];
+        norm = mk(drop.x - s.x, drop.y - s.y, drop.z - s.z);               // Sphere.cpp:67
+      }
+      else if (hit.slot < SM_PLANE_BIT)
       {
         const Triangle & tr = sc.tri[hit.slot - SM_TRI_BIT];
-        // tuvTrans * Vector3(u, v, 0): (u*_11 + v*_12) + 0*_13 with _13 == 0, Triangle.cpp:91
-        const float tx = (hit.u * tr.tuv[0] + hit.v * tr.tuv[1]) + 0.0f;
-        const float ty = (hit.u * tr.tuv[2] + hit.v * tr.tuv[3]) + 0.0f;
-        color = texSampleRef(&sc.tex[m.tex], sc.byteLut, tr.tu0 + tx, tr.tv0 + ty);
-      }
-    }
-    const V3 reflect = reflectVec(full, norm);
-    const float rayLen = vlen(ray);
-    const float normLen = vlen(norm);
-    const float reflectLen = vlen(reflect);
-    V3 sumLight = mk(0.0f, 0.0f, 0.0f);
-    V3 sumSpec = mk(0.0f, 0.0f, 0.0f);
-
-    for (int li = 0; li < sc.nL; li++)
-    {
-      const Light L = sc.light[li];
-      const V3 toLight = mk(L.ox - drop.x, L.oy - drop.y, L.oz - drop.z);
-      const float facing = vdot(toLight, norm);
-      if (facing > RFX_VSN)
-      {
-        const V3 sray = vadd(toLight, vscale(randDir, L.radius));        // Scene.cpp:129
-        nShadow++;
-        Best sh;
-        sh.dist = FLT_MAX; sh.slot = -1; sh.order = 0x7FFFFFFF; sh.t = 0; sh.u = 0; sh.v = 0; sh.ax = sh.ay = sh.az = 0;
-        intersectSmall(sc, drop, sray, 1u << hit.slot, sh);
-        const bool inShadow = sh.slot >= 0;
-        RFX_SIG(sig, 0x100 + 2 * li + (inShadow ? 1 : 0));
-
-        if (!inShadow)
+        norm = mk(tr.n[0], tr.n[1], tr.n[2]);
+        const int tex = m.tex;
+        if (tex >= 0)
         {
-          const float toLightLen = vlen(toLight);
-          float a = toLightLen * normLen;
-          const float lightDropCos = (a > RFX_VSN) ? facing / a : 0.0f;
-          if (L.power > RFX_VSN)
+          // tuvTrans * Vector3(u, v, 0): (u*_11 + v*_12) + 0*_13 with _13 == 0, Triangle.cpp:91
+          const float tx = (hit.u * tr.tuv[0] + hit.v * tr.tuv[1]) + 0.0f;
+          const float ty = (hit.u * tr.tuv[2] + hit.v * tr.tuv[3]) + 0.0f;
+          color = texSampleRef(&sc.tex[tex], sc.byteLut, tr.tu0 + tx, tr.tv0 + ty);
+        }
+      }
+      else
+      {
+        const Plane & pl = sc.pl[hit.slot - SM_PLANE_BIT];
+        norm = mk(pl.n[0], pl.n[1], pl.n[2]);
+      }
+      reflect = reflectVec(full, norm);
+      normLen = vlen(norm);
+      reflectLen = vlen(reflect);
+      sumLight = mk(0.0f, 0.0f, 0.0f);
+      sumSpec = mk(0.0f, 0.0f, 0.0f);
+      li = 0;
+    }
+    else
+    {
+      // ---- answer of the shadow query for light li, Scene.cpp:125-186
+      const Light & L = sc.light[li];
+      const bool inShadow = hit.slot >= 0;
+      if (SIG) RFX_SIG(sig, 0x100 + 2 * li + (inShadow ? 1 : 0));
+      if (!inShadow)
+      {
+        const float toLightLen = vlen(toLight);
+        float a = toLightLen * normLen;
+        const float lightDropCos = (a > RFX_VSN) ? facing / a : 0.0f;
+        if (L.power > RFX_VSN)
+        {
+          sumLight.x = sumLight.x + (L.r * lightDropCos) * L.power;       // Scene.cpp:156
+          sumLight.y = sumLight.y + (L.g * lightDropCos) * L.power;
+          sumLight.z = sumLight.z + (L.b * lightDropCos) * L.power;
+        }
+        a = vsqlen(toLight);
+        const float larsc = (a > RFX_VSN) ? 1.0f - L.radius * L.radius / a : 0.0f;   // Scene.cpp:160
+        if (larsc > 0)
+        {
+          // dropToLight.normalized(): same length value as toLightLen (same operations), Vector3.cpp:55-64
+          const V3 nl = (toLightLen > RFX_VSN) ? mk(toLight.x / toLightLen, toLight.y / toLightLen, toLight.z / toLightLen) : toLight;
+          const V3 dtl = vadd(nl, vscale(randDir, 1.0f - mrefl));
+          a = vlen(dtl) * reflectLen;
+          float rsc = (a > RFX_VSN) ? vdot(dtl, reflect) / a : 0.0f;
+          rsc = clamp01(rsc + (1.0f - sqrtf(larsc)));
+          if (rsc > RFX_VSN && L.radius > RFX_VSN)
           {
-            sumLight.x = sumLight.x + (L.r * lightDropCos) * L.power;     // Scene.cpp:156
-            sumLight.y = sumLight.y + (L.g * lightDropCos) * L.power;
-            sumLight.z = sumLight.z + (L.b * lightDropCos) * L.power;
-          }
-          a = vsqlen(toLight);
-          const float larsc = (a > RFX_VSN) ? 1.0f - L.radius * L.radius / a : 0.0f;   // Scene.cpp:160
-          if (larsc > 0)
-          {
-            // dropToLight.normalized(): same length value as toLightLen (same operations), Vector3.cpp:55-64
-            const V3 nl = (toLightLen > RFX_VSN) ? mk(toLight.x / toLightLen, toLight.y / toLightLen, toLight.z / toLightLen) : toLight;
-            const V3 dtl = vadd(nl, vscale(randDir, 1.0f - m.reflectivity));
-            a = vlen(dtl) * reflectLen;
-            float rsc = (a > RFX_VSN) ? vdot(dtl, reflect) / a : 0.0f;
-            rsc = clamp01(rsc + (1.0f - sqrtf(larsc)));
-            if (rsc > RFX_VSN && L.radius > RFX_VSN)
-            {
-              const float sp = powLikePowf(rsc, 1 + 3 * m.reflectivity * toLightLen / L.radius) * m.reflectivity;   // Scene.cpp:175
-              sumSpec.x = sumSpec.x + L.r * sp;
-              sumSpec.y = sumSpec.y + L.g * sp;
-              sumSpec.z = sumSpec.z + L.b * sp;
-            }
+            const float sp = powLikePowf(rsc, 1 + 3 * mrefl * toLightLen / L.radius) * mrefl;   // Scene.cpp:175
+            sumSpec.x = sumSpec.x + L.r * sp;
+            sumSpec.y = sumSpec.y + L.g * sp;
+            sumSpec.z = sumSpec.z + L.b * sp;
           }
         }
       }
+      li++;
     }
 
+    // ---- next light that faces the surface gets a shadow query, Scene.cpp:118-129
+    bool cast = false;
+    for (; li < sc.nL; li++)
+    {
+      const Light & L = sc.light[li];
+      toLight = mk(L.ox - drop.x, L.oy - drop.y, L.oz - drop.z);
+      facing = vdot(toLight, norm);
+      if (facing > RFX_VSN)
+      {
+        qd = vadd(toLight, vscale(randDir, L.radius));                    // Scene.cpp:129
+        cast = true;
+        break;
+      }
+    }
+    if (cast)
+    {
+      qo = drop; skip = hslot; shadowQuery = true;
+      nShadow++;
+      continue;
+    }
+
+    // ---- all lights answered: finish the hit, Scene.cpp:189-226
     sumLight = mk(sc.ambient[0] * sc.ambientPower + sumLight.x, sc.ambient[1] * sc.ambientPower + sumLight.y,
                   sc.ambient[2] * sc.ambientPower + sumLight.z);         // Scene.cpp:189
 
     float rf = 0.8f;                                                     // metal, Scene.cpp:207
-    if (m.type == 1)                                                     // dielectric, Scene.cpp:192-196
+    if (mtype == 1)                                                      // dielectric, Scene.cpp:192-196
     {
-      const float a = rayLen * normLen;
+      const float a = vlen(ray) * normLen;
       const float cosA = (a > RFX_VSN) ? clamp01(((ray.x * -norm.x + ray.y * -norm.y) + ray.z * -norm.z) / a) : 0.0f;
       rf = 0.2f + 0.8f * cubeLikePowf(1.0f - cosA);
     }
     const float k = 1.0f - rf;
     const V3 fin = mk(((color.x * k) * sumLight.x + sumSpec.x) * mul.x, ((color.y * k) * sumLight.y + sumSpec.y) * mul.y,
                       ((color.z * k) * sumLight.z + sumSpec.z) * mul.z); // Scene.cpp:198-199 / 209-210
-    if (m.type == 1) mul = vscale(mul, rf);                              // Scene.cpp:202
+    if (mtype == 1) mul = vscale(mul, rf);                               // Scene.cpp:202
     else mul = mk(mul.x * (color.x * rf), mul.y * (color.y * rf), mul.z * (color.z * rf));   // Scene.cpp:213
 
     pix = mk(clamp01(pix.x + fin.x), clamp01(pix.y + fin.y), clamp01(pix.z + fin.z));
 
     if (mul.x < 0.01f && mul.y < 0.01f && mul.z < 0.01f) break;
+    if (++refl >= reflNumber) break;
 
-    origin = drop;
-    ray = vadd(normalizeVec(reflect), vscale(randDir, 1.0f - m.reflectivity));   // Scene.cpp:226
+    ray = vadd(normalizeVec(reflect), vscale(randDir, 1.0f - mrefl));     // Scene.cpp:226
+    qo = drop; qd = ray; skip = -1; shadowQuery = false;
   }
   return pix;
 }
@@ -360,7 +315,58 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
 // ---- K2 ----------------------------------------------------------------------------------------------------------------
 constexpr int SMALL_THREADS = RFX_SMALL_THREADS;
 
+__device__ __forceinline__ void flushCounters(unsigned long long * __restrict__ counters, uint32_t nBounces, uint32_t nShadow, uint32_t warpId)
+{
+  // event counters: one striped atomic pair per warp
+  __syncwarp();
+  const uint32_t wb = __reduce_add_sync(0xffffffffu, nBounces);
+  const uint32_t ws = __reduce_add_sync(0xffffffffu, nShadow);
+  if ((threadIdx.x & 31) == 0 && counters)
+  {
+    const uint32_t slot = warpId & 31u;
+    atomicAdd(&counters[slot * 2], (unsigned long long)wb);
+    atomicAdd(&counters[slot * 2 + 1], (unsigned long long)ws);
+  }
+}
+
+// Fast kernel: a row-aligned slice (whole frame, band of rows, or this GPU's strips of a split frame), one sample per
+// pixel, no jitter, ARGB output only.  2-D grid: blockIdx.y = tile row, blockIdx.x * warps + warp = tile column.
 __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_small(const __grid_constant__ SmallScene sc, const __grid_constant__ FrameParams fp,
+                                                               const uint32_t * __restrict__ sampleStates, uint32_t * __restrict__ argbOut,
+                                                               unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1)
+{
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t x = (blockIdx.x * (SMALL_THREADS / 32) + warp) * RFX_TILE_W + (lane % RFX_TILE_W);
+  uint32_t y = y0 + blockIdx.y * RFX_TILE_H + (lane / RFX_TILE_W);
+  if (fp.stripWorld)
+  {
+    // split frame: the launch enumerates only this GPU's rows; compact row -> (own strip k, row in strip) -> frame row
+    const uint32_t k = y / fp.stripRows;
+    y = (k * fp.stripWorld + fp.stripRank) * fp.stripRows + (y % fp.stripRows);
+  }
+  const bool valid = x < fp.W && y < y1;
+  uint32_t nBounces = 0, nShadow = 0;
+  if (valid)
+  {
+    const uint32_t q = y * fp.W + x;                                     // < 2^32 for every frame size the API accepts
+    uint32_t s = __ldg(sampleStates + (q - y0 * fp.W));
+    const float rx = float(x) - fp.wHalf;                                // Render.cpp:154-155
+    const float ry = float(y) - fp.hHalf;
+    const V3 ray = mk((rx * fp.view[0] + ry * fp.view[1]) + fp.rz * fp.view[2],
+                      (rx * fp.view[3] + ry * fp.view[4]) + fp.rz * fp.view[5],
+                      (rx * fp.view[6] + ry * fp.view[7]) + fp.rz * fp.view[8]);
+    V3 rd;
+    rngTriple(s, rd.x, rd.y, rd.z);
+    uint32_t sig = 0;
+    const V3 c = traceSmall<false>(sc, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, nBounces, nShadow, sig);
+    argbOut[q] = packArgb(c.x, c.y, c.z);
+  }
+  flushCounters(counters, nBounces, nShadow, (blockIdx.y * gridDim.x + blockIdx.x) * (SMALL_THREADS / 32) + warp);
+}
+
+// General kernel: every mode of Render::renderNext (grid SSAA, block preview, additive jitter, arbitrary pixel slices,
+// float image, signatures).
+__global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_small_any(const __grid_constant__ SmallScene sc, const __grid_constant__ FrameParams fp,
                                                                const uint32_t * __restrict__ sampleStates, float * __restrict__ image,
                                                                uint32_t * __restrict__ argbOut, uint32_t * __restrict__ sigOut,
                                                                unsigned long long * __restrict__ counters, int tiled)
@@ -387,7 +393,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
   }
   else if (tiled)
   {
-    // row-aligned slice (a whole frame or a band of rows): 8x4 pixel tile per warp
+    // row-aligned slice (a whole frame or a band of rows): one pixel tile per warp
     const uint32_t tilesX = (fp.W + (RFX_TILE_W - 1u)) / RFX_TILE_W;
     const uint32_t y0 = (uint32_t)(fp.p0 / fp.W), y1 = (uint32_t)(fp.p1 / fp.W);
     const uint32_t warp = (uint32_t)(gid >> 5), lane = threadIdx.x & 31u;
@@ -395,7 +401,6 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
     y = y0 + (warp / tilesX) * RFX_TILE_H + (lane / RFX_TILE_W);
     if (fp.stripWorld)
     {
-      // split frame: the launch enumerates only this GPU's rows; compact row -> (own strip k, row in strip) -> frame row
       const uint32_t k = y / fp.stripRows;
       y = (k * fp.stripWorld + fp.stripRank) * fp.stripRows + (y % fp.stripRows);
     }
@@ -445,7 +450,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
       const V3 ray = mk((px * fp.view[0] + py * fp.view[1]) + fp.rz * fp.view[2],
                         (px * fp.view[3] + py * fp.view[4]) + fp.rz * fp.view[5],
                         (px * fp.view[6] + py * fp.view[7]) + fp.rz * fp.view[8]);
-      const V3 c = traceSmall(sc, eye, ray, fp.reflNum, rd, nBounces, nShadow, sig);
+      const V3 c = traceSmall<true>(sc, eye, ray, fp.reflNum, rd, nBounces, nShadow, sig);
       fin = blockMode ? c : vadd(fin, c);
       if (++ssy == sn) { ssy = 0; ssx++; }                  // ssx outer, ssy inner: the reference's summation order
     }
@@ -472,17 +477,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
         if (sigOut) sigOut[q] = sig;
       }
   }
-
-  // event counters: one striped atomic pair per warp
-  __syncwarp();
-  const uint32_t wb = __reduce_add_sync(0xffffffffu, nBounces);
-  const uint32_t ws = __reduce_add_sync(0xffffffffu, nShadow);
-  if ((threadIdx.x & 31) == 0 && counters)
-  {
-    const uint32_t slot = (blockIdx.x * (SMALL_THREADS / 32) + (threadIdx.x >> 5)) & 31u;
-    atomicAdd(&counters[slot * 2], (unsigned long long)wb);
-    atomicAdd(&counters[slot * 2 + 1], (unsigned long long)ws);
-  }
+  flushCounters(counters, nBounces, nShadow, blockIdx.x * (SMALL_THREADS / 32) + (threadIdx.x >> 5));
 }
 
 int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st)
@@ -503,6 +498,16 @@ int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st
         const uint64_t mine = nStrips > fp.stripRank ? (nStrips - fp.stripRank + fp.stripWorld - 1) / fp.stripWorld : 0;
         rows = mine * fp.stripRows;
       }
+      if (rows == 0) return 0;
+      const bool fast = fp.sampleNum == 1 && !fp.jitter && !w.image && !w.sigOut && w.argbOut && (uint64_t)fp.W * fp.H < (1ull << 32) &&
+                        (rows + RFX_TILE_H - 1) / RFX_TILE_H <= 65535u;
+      if (fast)
+      {
+        const uint32_t tilesX = (fp.W + RFX_TILE_W - 1) / RFX_TILE_W, warps = SMALL_THREADS / 32;
+        const dim3 grid((tilesX + warps - 1) / warps, (uint32_t)((rows + RFX_TILE_H - 1) / RFX_TILE_H));
+        k_trace_small<<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W));
+        return 1;
+      }
       nThreads = (uint64_t)((fp.W + RFX_TILE_W - 1) / RFX_TILE_W) * ((rows + RFX_TILE_H - 1) / RFX_TILE_H) * 32;
     }
     else
@@ -516,7 +521,7 @@ int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st
   }
   if (nThreads == 0) return 0;
   const uint32_t blocks = (uint32_t)((nThreads + SMALL_THREADS - 1) / SMALL_THREADS);
-  k_trace_small<<<blocks, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.image, w.argbOut, w.sigOut, w.counters, tiled);
+  k_trace_small_any<<<blocks, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.image, w.argbOut, w.sigOut, w.counters, tiled);
   return 1;
 }
 
