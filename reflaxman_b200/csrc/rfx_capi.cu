@@ -359,7 +359,14 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
       ss.sph[i] = make_float4(sph[i]->center[0], sph[i]->center[1], sph[i]->center[2], sph[i]->sqRadius);
       ss.mat[i] = sph[i]->mat;
     }
-    for (size_t i = 0; i < tri.size(); i++) { ss.tri[i] = tri[i]->tri; ss.mat[SMALL_MAX_SPHERES + i] = tri[i]->mat; }
+    for (size_t i = 0; i < tri.size(); i++)
+    {
+      const Triangle & t = tri[i]->tri;
+      ss.tri[i] = t; ss.mat[SMALL_MAX_SPHERES + i] = tri[i]->mat;
+      ss.triPk[i][0] = make_float4(t.v0[0], t.v0[1], t.v0[2], t.ax[6]);
+      ss.triPk[i][1] = make_float4(t.ax[7], t.ax[8], t.ax[0], t.ax[1]);
+      ss.triPk[i][2] = make_float4(t.ax[2], t.ax[3], t.ax[4], t.ax[5]);
+    }
     for (size_t i = 0; i < pla.size(); i++) { ss.pl[i] = pla[i]->plane; ss.mat[SMALL_MAX_SPHERES + SMALL_MAX_TRIS + i] = pla[i]->mat; }
     for (size_t i = 0; i < ctx->lights.size(); i++) ss.light[i] = ctx->lights[i];
     for (size_t i = 0; i < ctx->tex.size(); i++) { ss.tex[i].px = ctx->tex[i].dev; ss.tex[i].w = ctx->tex[i].w; ss.tex[i].h = ctx->tex[i].h; }

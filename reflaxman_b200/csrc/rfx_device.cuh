@@ -96,11 +96,70 @@ __device__ __forceinline__ float cubeLikePowf(float x)
   return (float)((d * d) * d);
 }
 
-// powf(x, y) of Scene.cpp:175 (specular lobe, x in (0, 1], y >= 1): double-precision pow rounded once to float, i.e. the
-// correctly rounded value in all but ~1e-8 of cases; glibc's powf is within 0.52 ulp of it.
-static __device__ __noinline__ float powLikePowf(float x, float y)
+// powf(x, y) of Scene.cpp:175 (specular lobe: x in (2^-63, 1], y >= 1).  glibc's powf is correctly rounded in all but a
+// vanishing fraction of cases, so the target is RN_float(x^y).  Evaluated in binary64 as 2^(y*log2 x) with ~2^-50 relative
+// error, rounded once to float: wrong only when x^y lies within 2^-26 relative of a float rounding boundary, about one
+// call in 10^7 (tools/pow_check.cu measures it against CUDA's correctly-rounded-to-double pow()).  It replaces CUDA's
+// pow(double, double), whose 1500 instructions of special-case and extended-precision code evicted the kernel's working
+// set from the 32 KB instruction cache.  Requires 0 < x < inf; any finite y.
+static __device__ __noinline__ float powLikePowf(float xf, float yf)
 {
-  return (float)pow((double)x, (double)y);
+  const double x = (double)xf;                      // exact; float denormals are normal doubles
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000FFFFF) | 0x3FF00000;              // m in [1, 2)
+  if (hi >= 0x3FF6A09F) { hi -= 0x00100000; e += 1; }   // m in [sqrt(1/2), sqrt(2))
+  const double m = __hiloint2double(hi, lo);
+  // s = (m - 1) / (m + 1): reciprocal seed + two Newton steps, then one residual correction of the quotient
+  const double f = m - 1.0, g = m + 1.0;
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(g));
+  r = fma(r, fma(-g, r, 1.0), r);
+  r = fma(r, fma(-g, r, 1.0), r);
+  double s = f * r;
+  s = fma(r, fma(-g, s, f), s);
+  // ln m = 2 atanh(s) = 2s (1 + s^2/3 + s^4/5 + ...), |s| <= 0.1716: 11 terms leave a 6e-19 relative tail
+  const double s2 = s * s;
+  double p = 1.0 / 23.0;
+  p = fma(p, s2, 1.0 / 21.0);
+  p = fma(p, s2, 1.0 / 19.0);
+  p = fma(p, s2, 1.0 / 17.0);
+  p = fma(p, s2, 1.0 / 15.0);
+  p = fma(p, s2, 1.0 / 13.0);
+  p = fma(p, s2, 1.0 / 11.0);
+  p = fma(p, s2, 1.0 / 9.0);
+  p = fma(p, s2, 1.0 / 7.0);
+  p = fma(p, s2, 1.0 / 5.0);
+  p = fma(p, s2, 1.0 / 3.0);
+  const double lnm = fma(s * s2, p, s) * 2.0;       // 2s + 2s^3 p
+  // log2 x = e + ln m * log2(e), log2(e) split into a 32-bit head and a tail so that the head product is exact enough
+  const double L = fma(lnm, 1.4426950408889634074, (double)e);
+  double z = (double)yf * L;
+  if (!(z > -1000.0)) z = -1000.0;                  // x^y underflows binary32 long before (also absorbs -inf)
+  if (!(z < 1000.0)) z = 1000.0;
+  const double n = rint(z);
+  const double t = (z - n) * 0.69314718055994530942;   // |t| <= 0.3466
+  double q = 1.0 / 6227020800.0;                    // Taylor of e^t to t^13: 4e-18 relative tail
+  q = fma(q, t, 1.0 / 479001600.0);
+  q = fma(q, t, 1.0 / 39916800.0);
+  q = fma(q, t, 1.0 / 3628800.0);
+  q = fma(q, t, 1.0 / 362880.0);
+  q = fma(q, t, 1.0 / 40320.0);
+  q = fma(q, t, 1.0 / 5040.0);
+  q = fma(q, t, 1.0 / 720.0);
+  q = fma(q, t, 1.0 / 120.0);
+  q = fma(q, t, 1.0 / 24.0);
+  q = fma(q, t, 1.0 / 6.0);
+  q = fma(q, t, 0.5);
+  q = fma(q, t, 1.0);
+  q = fma(q, t, 1.0);
+  // scale by 2^n in two steps so that neither factor leaves the binary64 normal range (|n| <= 1000)
+  const int ni = (int)n;
+  const int n1 = ni / 2, n2 = ni - n1;
+  q = q * __hiloint2double((n1 + 1023) << 20, 0);
+  q = q * __hiloint2double((n2 + 1023) << 20, 0);
+  return (float)q;                                  // cvt.rn.f32.f64: one rounding, also into the float denormal range
 }
 
 __device__ __forceinline__ float clamp01(float v) { return v < 0.0f ? 0.0f : v > 1.0f ? 1.0f : v; }   // trace_math.h:24
@@ -116,23 +175,17 @@ __device__ __forceinline__ V3 texel(const TexRef & t, const float * __restrict__
   return mk(__ldg(lut + ((c >> 16) & 0xFFu)), __ldg(lut + ((c >> 8) & 0xFFu)), __ldg(lut + (c & 0xFFu)));
 }
 
-// t == nullptr or t->px == nullptr: empty texture -> the reference's grey checker (Texture.cpp:242-243)
-static __device__ __noinline__ V3 texSampleRef(const TexRef * t, const float * __restrict__ lut, float u, float v)
+// non-empty texture, (u, v) already known to lie in [0, 1]: Texture.cpp:246-268
+static __device__ __noinline__ V3 texSampleBilinear(const TexRef & t, const float * __restrict__ lut, float u, float v)
 {
-  if (u < 0.0f || u > 1.0f || v < 0.0f || v > 1.0f) return mk(0.0f, 0.0f, 0.0f);
-  if (!t || !t->px)
-  {
-    const float g = ((int(u * 50) % 2) ^ (int(v * 50) % 2)) ? 0.5f : 0.75f;   // Texture.cpp:243
-    return mk(g, g, g);
-  }
-  const float cu = u < 0.0f ? 0.0f : u > (1.0f - FLT_EPSILON) ? (1.0f - FLT_EPSILON) : u;
-  const float cv = v < 0.0f ? 0.0f : v > (1.0f - FLT_EPSILON) ? (1.0f - FLT_EPSILON) : v;
-  const float fx = cu * float(t->w);
-  const float fy = cv * float(t->h);
+  const float cu = u > (1.0f - FLT_EPSILON) ? (1.0f - FLT_EPSILON) : u;
+  const float cv = v > (1.0f - FLT_EPSILON) ? (1.0f - FLT_EPSILON) : v;
+  const float fx = cu * float(t.w);
+  const float fy = cv * float(t.h);
   const uint32_t x = (uint32_t)fx, y = (uint32_t)fy;
-  if (x < t->w - 1 && y < t->h - 1)
+  if (x < t.w - 1 && y < t.h - 1)
   {
-    const V3 c00 = texel(*t, lut, x, y), c01 = texel(*t, lut, x, y + 1), c10 = texel(*t, lut, x + 1, y), c11 = texel(*t, lut, x + 1, y + 1);
+    const V3 c00 = texel(t, lut, x, y), c01 = texel(t, lut, x, y + 1), c10 = texel(t, lut, x + 1, y), c11 = texel(t, lut, x + 1, y + 1);
     const float uf = fx - floorf(fx), vf = fy - floorf(fy);
     const float uo = 1 - uf, vo = 1 - vf;
     // (c00*uo + c10*uf)*vo + (c01*uo + c11*uf)*vf, Texture.cpp:264
@@ -140,11 +193,27 @@ static __device__ __noinline__ V3 texSampleRef(const TexRef * t, const float * _
               (c00.y * uo + c10.y * uf) * vo + (c01.y * uo + c11.y * uf) * vf,
               (c00.z * uo + c10.z * uf) * vo + (c01.z * uo + c11.z * uf) * vf);
   }
-  if (x >= t->w || y >= t->h) return mk(0.0f, 0.0f, 0.0f);   // Texture.cpp:223-224 (unreachable after the clamp)
-  return texel(*t, lut, x, y);
+  if (x >= t.w || y >= t.h) return mk(0.0f, 0.0f, 0.0f);   // Texture.cpp:223-224 (unreachable after the clamp)
+  return texel(t, lut, x, y);
 }
 
-// direction -> (u, v) in the 4x3 cube-cross atlas, Skybox.cpp:39-103
+// t == nullptr or t->px == nullptr: empty texture -> the reference's grey checker (Texture.cpp:242-243); the checker and
+// the range test are inlined at the call sites, the texel path is a shared subroutine
+__device__ __forceinline__ V3 texSampleRef(const TexRef * t, const float * __restrict__ lut, float u, float v)
+{
+  if (u < 0.0f || u > 1.0f || v < 0.0f || v > 1.0f) return mk(0.0f, 0.0f, 0.0f);
+  if (!t || !t->px)
+  {
+    // int(u*50) % 2 ^ int(v*50) % 2 with u*50, v*50 in [0, 50]: the truncated values are non-negative, so % 2 is & 1
+    const float g = ((int(u * 50) ^ int(v * 50)) & 1) ? 0.5f : 0.75f;   // Texture.cpp:243
+    return mk(g, g, g);
+  }
+  return texSampleBilinear(*t, lut, u, v);
+}
+
+// direction -> (u, v) in the 4x3 cube-cross atlas, Skybox.cpp:39-103.  Every face evaluates centre +- (p / major) * halfTile;
+// a - q*h == a + ((-p)/m)*h bit for bit (negation commutes with IEEE division, multiplication and turns + into -), so the
+// face only selects operands and the two divisions are issued once instead of once per face.
 __device__ __forceinline__ void skyDirToUv(V3 ray, float hw, float hh, float & u, float & v)
 {
   const float uLeft = 1.0f / 8.0f, vMid = 3.0f / 6.0f, uFront = 3.0f / 8.0f, uRight = 5.0f / 8.0f, uBack = 7.0f / 8.0f;
@@ -152,21 +221,27 @@ __device__ __forceinline__ void skyDirToUv(V3 ray, float hw, float hh, float & u
   const V3 n = normalizeVec(ray);
   const float x = n.x, y = n.y, z = n.z;
   const float ax = fabsf(x) + RFX_VSN, ay = fabsf(y) + RFX_VSN, az = fabsf(z) + RFX_VSN;
+  float pu, pv, major, cu, cv;
   if (az >= ax && az >= ay)
   {
-    if (z > 0) { u = uFront + x / az * hw; v = vMid + y / az * hh; }
-    else       { u = uBack - x / az * hw;  v = vMid + y / az * hh; }
+    major = az; pv = y; cv = vMid;
+    if (z > 0) { pu = x; cu = uFront; }          // u = uFront + x / az * hw; v = vMid + y / az * hh
+    else       { pu = -x; cu = uBack; }          // u = uBack - x / az * hw
   }
   else if (ax >= ay && ax >= az)
   {
-    if (x > 0) { u = uRight - z / ax * hw; v = vMid + y / ax * hh; }
-    else       { u = uLeft + z / ax * hw;  v = vMid + y / ax * hh; }
+    major = ax; pv = y; cv = vMid;
+    if (x > 0) { pu = -z; cu = uRight; }         // u = uRight - z / ax * hw; v = vMid + y / ax * hh
+    else       { pu = z; cu = uLeft; }           // u = uLeft + z / ax * hw
   }
   else
   {
-    if (y > 0) { u = uFront + x / ay * hw; v = vTop - z / ay * hh; }      // uTop == uFront == uBottom == 3/8
-    else       { u = uFront + x / ay * hw; v = vBottom + z / ay * hh; }
+    major = ay; pu = x; cu = uFront;             // uTop == uFront == uBottom == 3/8: u = uFront + x / ay * hw
+    if (y > 0) { pv = -z; cv = vTop; }           // v = vTop - z / ay * hh
+    else       { pv = z; cv = vBottom; }         // v = vBottom + z / ay * hh
   }
+  u = cu + pu / major * hw;
+  v = cv + pv / major * hh;
 }
 
 

@@ -30,11 +30,14 @@ namespace rfx
 #define RFX_TILE_W 4u      // pixel tile of one warp: RFX_TILE_W x RFX_TILE_H = 32 (4x8 measured best, profiles/variants_d_r1.jsonl)
 #endif
 #define RFX_TILE_H (32u / RFX_TILE_W)
+#ifndef RFX_SPHERE_PAIRS
+#define RFX_SPHERE_PAIRS 0
+#endif
 #ifndef RFX_SMALL_THREADS
-#define RFX_SMALL_THREADS 256
+#define RFX_SMALL_THREADS 128
 #endif
 #ifndef RFX_SMALL_MINBLOCKS
-#define RFX_SMALL_MINBLOCKS 3
+#define RFX_SMALL_MINBLOCKS 7
 #endif
 
 constexpr int SM_TRI_BIT = SMALL_MAX_SPHERES;                       // object slots: spheres | triangles | planes
@@ -64,53 +67,97 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
 {
   const float a = vsqlen(d);                                          // Sphere.cpp:50
   const float r2x = d.x * 2.0f, r2y = d.y * 2.0f, r2z = d.z * 2.0f;   // 2.0f * ray, Sphere.cpp:51
-  const float a4 = 4.0f * a, a2 = 2.0f * a;                           // Sphere.cpp:53,57
-  const bool aOk = a > RFX_VSN;                                       // Sphere.cpp:55 `a > VERY_SMALL_NUMBER`
+  const float a2 = 2.0f * a;                                          // Sphere.cpp:57
+  // A lane that must not take any (more) sphere hit — a <= 2^-63 (Sphere.cpp:55), or an any-hit query that has found its
+  // occluder — gets a NaN in place of 4a: its discriminant becomes NaN and fails `disc >= 0` without an extra predicate
+  float a4 = (a > RFX_VSN) ? 4.0f * a : __int_as_float(0x7FC00000);  // Sphere.cpp:53
 
   // ---- spheres: discriminant of Sphere.cpp:49-53 with the per-ray invariants hoisted.  t = (-b - sqrt(disc)) / 2a can
-  // only exceed 2^-63 when b < 0 (sqrt >= 0, 2a > 0), so lanes with b >= 0 never enter the tail — same decisions, fewer sqrt
-  const int nS = sc.nS;
-#pragma unroll 1
-  for (int i = 0; i < nS; i++)
-  {
-    const float4 s = sc.sph[i];
-    const float vx = o.x - s.x, vy = o.y - s.y, vz = o.z - s.z;
-    const float b = (r2x * vx + r2y * vy) + r2z * vz;
-    const float c = ((vx * vx + vy * vy) + vz * vz) - s.w;
-    const float disc = b * b - a4 * c;
-    if (disc >= 0.0f && b < 0.0f && aOk && i != skip && !(anyHit && best.slot >= 0))
-    {
-      const float t = (-b - sqrtf(disc)) / a2;                        // Sphere.cpp:57
-      if (t > RFX_VSN)
-      {
-        const float fx = d.x * t, fy = d.y * t, fz = d.z * t;
-        const float dist = sqrtf((fx * fx + fy * fy) + fz * fz);      // fullRay.length(), Sphere.cpp:62
-        if (dist > RFX_DELTA) considerHit(best, dist, i, sc.mat[i].order, t, 0.0f, 0.0f);
-      }
+  // only exceed 2^-63 when b < 0 (sqrt >= 0, 2a > 0), so lanes with b >= 0 never enter the tail — same decisions, fewer sqrt.
+  const char * sphBase = reinterpret_cast<const char *>(sc.sph);
+  const char * ordBase = reinterpret_cast<const char *>(&sc.mat[0].order);
+  const int skipOff = skip << 4;
+  // One induction variable: the byte offset of sphere i inside sc.sph (16 B each; Material is 32 B).
+#define RFX_SPHERE_REJECT(OFF, S, B, DISC)                                                   \
+    const float4 S = *reinterpret_cast<const float4 *>(sphBase + (OFF));                     \
+    float B, DISC;                                                                           \
+    {                                                                                        \
+      const float vx = o.x - S.x, vy = o.y - S.y, vz = o.z - S.z;                            \
+      B = (r2x * vx + r2y * vy) + r2z * vz;                                                  \
+      const float c = ((vx * vx + vy * vy) + vz * vz) - S.w;                                 \
+      DISC = B * B - a4 * c;                                                                 \
     }
+#define RFX_SPHERE_TAIL(OFF, B, DISC)                                                        \
+    if (DISC >= 0.0f && B < 0.0f && (OFF) != skipOff)                                        \
+    {                                                                                        \
+      const float t = (-B - sqrtf(DISC)) / a2;                        /* Sphere.cpp:57 */    \
+      if (t > RFX_VSN)                                                                       \
+      {                                                                                      \
+        const float fx = d.x * t, fy = d.y * t, fz = d.z * t;                                \
+        const float dist = sqrtf((fx * fx + fy * fy) + fz * fz);      /* fullRay.length(), Sphere.cpp:62 */ \
+        if (dist > RFX_DELTA)                                                                \
+        {                                                                                    \
+          considerHit(best, dist, (OFF) >> 4, *reinterpret_cast<const int *>(ordBase + 2 * (OFF)), t, 0.0f, 0.0f); \
+          if (anyHit) a4 = __int_as_float(0x7FC00000);                                       \
+        }                                                                                    \
+      }                                                                                      \
+    }
+  const int endOff = sc.nS << 4;
+  int off = 0;
+#if RFX_SPHERE_PAIRS
+  // two spheres per trip: the two reject chains are independent (ILP for a scheduler with ~6 resident warps) and share the
+  // loop bookkeeping; the second sphere's discriminant is evaluated before the first tail, so an any-hit lane that closes in
+  // the first tail re-poisons it explicitly
+  const int endPair = endOff & ~31;
+#pragma unroll 1
+  for (; off != endPair; off += 32)
+  {
+    asm volatile("" : "+r"(off));
+    RFX_SPHERE_REJECT(off, s0, b0, disc0)
+    RFX_SPHERE_REJECT(off + 16, s1, b1, disc1)
+    RFX_SPHERE_TAIL(off, b0, disc0)
+    if (a4 != a4) disc1 = a4;
+    RFX_SPHERE_TAIL(off + 16, b1, disc1)
   }
+#endif
+#pragma unroll 1
+  for (; off != endOff; off += 16)
+  {
+    asm volatile("" : "+r"(off));   // keeps `off` the only induction variable (ptxas otherwise strength-reduces it into five)
+    RFX_SPHERE_REJECT(off, s0, b0, disc0)
+    RFX_SPHERE_TAIL(off, b0, disc0)
+  }
+#undef RFX_SPHERE_REJECT
+#undef RFX_SPHERE_TAIL
 
   // ---- triangles: third row of axTrans*(origin - v0) and axTrans*ray (Triangle.cpp:56-57, Matrix33.cpp:232-234);
-  // t = -oz/rz > 2^-63 needs |rz| > 2^-63 and oz, rz of strictly opposite sign (the sign of an IEEE quotient is exact),
-  // so everything else is skipped without dividing
-  const int nT = sc.nT;
+  // t = -oz/rz > 2^-63 needs |rz| > 2^-63 and oz, rz of opposite sign (the sign of an IEEE quotient is exact; a zero oz
+  // gives t = 0 and fails in the tail), so everything else is skipped without dividing.  A closed lane (any-hit query
+  // that has its occluder) carries +inf as the |rz| threshold.
+  float rzMin = (anyHit && best.slot >= 0) ? __int_as_float(0x7F800000) : RFX_VSN;
+  const char * triBase = reinterpret_cast<const char *>(sc.triPk);
+  const char * triOrd = reinterpret_cast<const char *>(&sc.mat[SM_TRI_BIT].order);
+  const int skipTri = (skip - SM_TRI_BIT) * 48;
+  const int endTri = sc.nT * 48;
 #pragma unroll 1
-  for (int k = 0; k < nT; k++)
+  for (int off = 0; off != endTri; off += 48)
   {
-    const Triangle & tr = sc.tri[k];
-    const float px = o.x - tr.v0[0], py = o.y - tr.v0[1], pz = o.z - tr.v0[2];
-    const float oz = (px * tr.ax[6] + py * tr.ax[7]) + pz * tr.ax[8];
-    const float rz = (d.x * tr.ax[6] + d.y * tr.ax[7]) + d.z * tr.ax[8];
-    if (fabsf(rz) > RFX_VSN && ((oz < 0.0f && rz > 0.0f) || (oz > 0.0f && rz < 0.0f)) && (SM_TRI_BIT + k) != skip &&
-        !(anyHit && best.slot >= 0))
+    asm volatile("" : "+r"(off));
+    const float4 A = *reinterpret_cast<const float4 *>(triBase + off);
+    const float4 B = *reinterpret_cast<const float4 *>(triBase + off + 16);
+    const float px = o.x - A.x, py = o.y - A.y, pz = o.z - A.z;
+    const float oz = (px * A.w + py * B.x) + pz * B.y;
+    const float rz = (d.x * A.w + d.y * B.x) + d.z * B.y;
+    if ((__float_as_int(oz) ^ __float_as_int(rz)) < 0 && fabsf(rz) > rzMin && off != skipTri)
     {
       const float t = -oz / rz;                                       // Triangle.cpp:61
       if (t > RFX_VSN)
       {
-        const float ox = (px * tr.ax[0] + py * tr.ax[1]) + pz * tr.ax[2];
-        const float rx = (d.x * tr.ax[0] + d.y * tr.ax[1]) + d.z * tr.ax[2];
-        const float oy = (px * tr.ax[3] + py * tr.ax[4]) + pz * tr.ax[5];
-        const float ry = (d.x * tr.ax[3] + d.y * tr.ax[4]) + d.z * tr.ax[5];
+        const float4 C = *reinterpret_cast<const float4 *>(triBase + off + 32);
+        const float ox = (px * B.z + py * B.w) + pz * C.x;
+        const float rx = (d.x * B.z + d.y * B.w) + d.z * C.x;
+        const float oy = (px * C.y + py * C.z) + pz * C.w;
+        const float ry = (d.x * C.y + d.y * C.z) + d.z * C.w;
         const float u = ox + t * rx;                                  // Triangle.cpp:65-66
         const float v = oy + t * ry;
         if (u >= 0.0f && v >= 0.0f && u + v < 1.0f)
@@ -118,7 +165,11 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
           const float fx = d.x * t, fy = d.y * t, fz = d.z * t;
           const float sq = (fx * fx + fy * fy) + fz * fz;
           if (sq > RFX_DELTA * RFX_DELTA)
-            considerHit(best, sqrtf(sq), SM_TRI_BIT + k, sc.mat[SM_TRI_BIT + k].order, t, u, v);
+          {
+            const int k = off / 48;
+            considerHit(best, sqrtf(sq), SM_TRI_BIT + k, *reinterpret_cast<const int *>(triOrd + k * 32), t, u, v);
+            if (anyHit) rzMin = __int_as_float(0x7F800000);
+          }
         }
       }
     }
@@ -148,56 +199,57 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
 }
 
 // ---- Scene::trace (reference Scene.cpp:73-236) ------------------------------------------------------------------------
+// `events` counts bounce-loop iterations in its low half and shadow rays in its high half (one register instead of two).
 template <bool SIG>
-__device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ray, int reflNumber, V3 randDir,
-                                         uint32_t & nBounces, uint32_t & nShadow, uint32_t & sig)
+__device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ray, int reflNumber, V3 randDir, uint32_t & events, uint32_t & sig)
 {
   V3 mul = mk(1.0f, 1.0f, 1.0f);
   V3 pix = mk(0.0f, 0.0f, 0.0f);
   if (reflNumber <= 0) return pix;
 
-  // the query in flight: (qo, qd), ignoring slot `skip`; shadowQuery says which of the two states the lane is in
+  // The query in flight is (qo, qd).  Bounce state: qo = origin, qd = ray of the reference's loop.  Shadow state
+  // (hslot >= 0 and shadowQuery): qo = drop, qd = the jittered ray towards light li, the hit object is ignored.
   V3 qo = origin, qd = ray;
-  int skip = -1;
   bool shadowQuery = false;
   int refl = 0, li = 0, hslot = -1;
-  // state of the hit being shaded, alive across its shadow queries
-  V3 drop = origin, norm = ray, reflect = ray, color = mul, sumLight = pix, sumSpec = pix, toLight = ray;
-  float facing = 0.0f, normLen = 0.0f, reflectLen = 0.0f, mrefl = 0.0f;
-  int mtype = 0;
+  // what survives of the hit while its lights are being answered
+  V3 norm = ray, reflect = ray, color = mul, sumLight = pix, sumSpec = pix;
+  float normLen = 0.0f, reflectLen = 0.0f, mrefl = 0.0f;
+  float rf = 0.0f;          // weight of the reflected continuation (Scene.cpp:196 / :207); its sign bit clear
+  bool dielectric = false;
 
   for (;;)
   {
     Best hit;
     hit.dist = FLT_MAX; hit.slot = -1; hit.order = 0x7FFFFFFF; hit.t = 0; hit.u = 0; hit.v = 0;
-    intersectSmall(sc, qo, qd, skip, shadowQuery, hit);
+    intersectSmall(sc, qo, qd, shadowQuery ? hslot : -1, shadowQuery, hit);
 
     if (!shadowQuery)
     {
       // ---- closest hit of the bounce segment (origin = qo, ray = qd), Scene.cpp:80-112
-      nBounces++;
+      events++;
       if (hit.slot < 0)
       {
         if (SIG) RFX_SIG(sig, 0xFFFF);
         float u, v;
-        skyDirToUv(ray, sc.halfTileW, sc.halfTileH, u, v);
+        skyDirToUv(qd, sc.halfTileW, sc.halfTileH, u, v);
         const V3 sky = texSampleRef(sc.skyTex >= 0 ? &sc.tex[sc.skyTex] : nullptr, sc.byteLut, u, v);
         pix = mk(clamp01(pix.x + (mul.x * sky.x) * sc.env[0]), clamp01(pix.y + (mul.y * sky.y) * sc.env[1]),
                  clamp01(pix.z + (mul.z * sky.z) * sc.env[2]));            // Scene.cpp:230-231
         break;
       }
       if (SIG) RFX_SIG(sig, hit.order + 1);
-      const V3 full = vscale(ray, hit.t);
-      drop = vadd(qo, full);
+      const V3 full = vscale(qd, hit.t);
+      qo = vadd(qo, full);                                                 // drop point: origin of everything that follows
       const Material & m = sc.mat[hit.slot];
       color = mk(m.r, m.g, m.b);
       mrefl = m.reflectivity;
-      mtype = m.type;
+      dielectric = m.type == 1;
       hslot = hit.slot;
       if (hit.slot < SM_TRI_BIT)
       {
         const float4 s = sc.sph[hit.slot];
-        norm = mk(drop.x - s.x, drop.y - s.y, drop.z - s.z);               // Sphere.cpp:67
+        norm = mk(qo.x - s.x, qo.y - s.y, qo.z - s.z);                     // Sphere.cpp:67
       }
       else if (hit.slot < SM_PLANE_BIT)
       {
@@ -220,6 +272,14 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
       reflect = reflectVec(full, norm);
       normLen = vlen(norm);
       reflectLen = vlen(reflect);
+      // the continuation weight only depends on ray and norm: evaluate it while the ray is still in registers
+      rf = 0.8f;                                                           // metal, Scene.cpp:207
+      if (dielectric)                                                      // Scene.cpp:192-196
+      {
+        const float a = vlen(qd) * normLen;
+        const float cosA = (a > RFX_VSN) ? clamp01(((qd.x * -norm.x + qd.y * -norm.y) + qd.z * -norm.z) / a) : 0.0f;
+        rf = 0.2f + 0.8f * cubeLikePowf(1.0f - cosA);
+      }
       sumLight = mk(0.0f, 0.0f, 0.0f);
       sumSpec = mk(0.0f, 0.0f, 0.0f);
       li = 0;
@@ -232,6 +292,8 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
       if (SIG) RFX_SIG(sig, 0x100 + 2 * li + (inShadow ? 1 : 0));
       if (!inShadow)
       {
+        const V3 toLight = mk(L.ox - qo.x, L.oy - qo.y, L.oz - qo.z);     // the same subtractions as before the query
+        const float facing = vdot(toLight, norm);
         const float toLightLen = vlen(toLight);
         float a = toLightLen * normLen;
         const float lightDropCos = (a > RFX_VSN) ? facing / a : 0.0f;
@@ -268,9 +330,8 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
     for (; li < sc.nL; li++)
     {
       const Light & L = sc.light[li];
-      toLight = mk(L.ox - drop.x, L.oy - drop.y, L.oz - drop.z);
-      facing = vdot(toLight, norm);
-      if (facing > RFX_VSN)
+      const V3 toLight = mk(L.ox - qo.x, L.oy - qo.y, L.oz - qo.z);
+      if (vdot(toLight, norm) > RFX_VSN)
       {
         qd = vadd(toLight, vscale(randDir, L.radius));                    // Scene.cpp:129
         cast = true;
@@ -279,26 +340,18 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
     }
     if (cast)
     {
-      qo = drop; skip = hslot; shadowQuery = true;
-      nShadow++;
+      shadowQuery = true;
+      events += 0x10000u;
       continue;
     }
 
     // ---- all lights answered: finish the hit, Scene.cpp:189-226
     sumLight = mk(sc.ambient[0] * sc.ambientPower + sumLight.x, sc.ambient[1] * sc.ambientPower + sumLight.y,
                   sc.ambient[2] * sc.ambientPower + sumLight.z);         // Scene.cpp:189
-
-    float rf = 0.8f;                                                     // metal, Scene.cpp:207
-    if (mtype == 1)                                                      // dielectric, Scene.cpp:192-196
-    {
-      const float a = vlen(ray) * normLen;
-      const float cosA = (a > RFX_VSN) ? clamp01(((ray.x * -norm.x + ray.y * -norm.y) + ray.z * -norm.z) / a) : 0.0f;
-      rf = 0.2f + 0.8f * cubeLikePowf(1.0f - cosA);
-    }
     const float k = 1.0f - rf;
     const V3 fin = mk(((color.x * k) * sumLight.x + sumSpec.x) * mul.x, ((color.y * k) * sumLight.y + sumSpec.y) * mul.y,
                       ((color.z * k) * sumLight.z + sumSpec.z) * mul.z); // Scene.cpp:198-199 / 209-210
-    if (mtype == 1) mul = vscale(mul, rf);                               // Scene.cpp:202
+    if (dielectric) mul = vscale(mul, rf);                               // Scene.cpp:202
     else mul = mk(mul.x * (color.x * rf), mul.y * (color.y * rf), mul.z * (color.z * rf));   // Scene.cpp:213
 
     pix = mk(clamp01(pix.x + fin.x), clamp01(pix.y + fin.y), clamp01(pix.z + fin.z));
@@ -306,8 +359,8 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
     if (mul.x < 0.01f && mul.y < 0.01f && mul.z < 0.01f) break;
     if (++refl >= reflNumber) break;
 
-    ray = vadd(normalizeVec(reflect), vscale(randDir, 1.0f - mrefl));     // Scene.cpp:226
-    qo = drop; qd = ray; skip = -1; shadowQuery = false;
+    qd = vadd(normalizeVec(reflect), vscale(randDir, 1.0f - mrefl));      // Scene.cpp:226
+    shadowQuery = false;
   }
   return pix;
 }
@@ -317,6 +370,7 @@ constexpr int SMALL_THREADS = RFX_SMALL_THREADS;
 
 __device__ __forceinline__ void flushCounters(unsigned long long * __restrict__ counters, uint32_t nBounces, uint32_t nShadow, uint32_t warpId)
 {
+  if (!counters) return;   // uniform
   // event counters: one striped atomic pair per warp
   __syncwarp();
   const uint32_t wb = __reduce_add_sync(0xffffffffu, nBounces);
@@ -345,7 +399,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
     y = (k * fp.stripWorld + fp.stripRank) * fp.stripRows + (y % fp.stripRows);
   }
   const bool valid = x < fp.W && y < y1;
-  uint32_t nBounces = 0, nShadow = 0;
+  uint32_t events = 0;
   if (valid)
   {
     const uint32_t q = y * fp.W + x;                                     // < 2^32 for every frame size the API accepts
@@ -358,10 +412,10 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
     V3 rd;
     rngTriple(s, rd.x, rd.y, rd.z);
     uint32_t sig = 0;
-    const V3 c = traceSmall<false>(sc, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, nBounces, nShadow, sig);
+    const V3 c = traceSmall<false>(sc, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, events, sig);
     argbOut[q] = packArgb(c.x, c.y, c.z);
   }
-  flushCounters(counters, nBounces, nShadow, (blockIdx.y * gridDim.x + blockIdx.x) * (SMALL_THREADS / 32) + warp);
+  flushCounters(counters, events & 0xFFFFu, events >> 16, (blockIdx.y * gridDim.x + blockIdx.x) * (SMALL_THREADS / 32) + warp);
 }
 
 // General kernel: every mode of Render::renderNext (grid SSAA, block preview, additive jitter, arbitrary pixel slices,
@@ -450,7 +504,9 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
       const V3 ray = mk((px * fp.view[0] + py * fp.view[1]) + fp.rz * fp.view[2],
                         (px * fp.view[3] + py * fp.view[4]) + fp.rz * fp.view[5],
                         (px * fp.view[6] + py * fp.view[7]) + fp.rz * fp.view[8]);
-      const V3 c = traceSmall<true>(sc, eye, ray, fp.reflNum, rd, nBounces, nShadow, sig);
+      uint32_t events = 0;
+      const V3 c = traceSmall<true>(sc, eye, ray, fp.reflNum, rd, events, sig);
+      nBounces += events & 0xFFFFu; nShadow += events >> 16;
       fin = blockMode ? c : vadd(fin, c);
       if (++ssy == sn) { ssy = 0; ssx++; }                  // ssx outer, ssy inner: the reference's summation order
     }

@@ -83,6 +83,9 @@ struct SmallScene
   const float * byteLut;
   float4 sph[SMALL_MAX_SPHERES];            // cx, cy, cz, r^2
   Triangle tri[SMALL_MAX_TRIS];
+  // the same triangles repacked for 64-bit constant loads in the intersection loop:
+  // [0] = v0.x v0.y v0.z ax[6]   [1] = ax[7] ax[8] ax[0] ax[1]   [2] = ax[2] ax[3] ax[4] ax[5]
+  float4 triPk[SMALL_MAX_TRIS][3];
   Plane pl[SMALL_MAX_PLANES];
   Light light[SMALL_MAX_LIGHTS];
   Material mat[SMALL_MAX_OBJECTS];          // indexed by candidate-mask bit: spheres 0.., triangles 16.., planes 24..

@@ -11,20 +11,29 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 
 VARIANTS = {
     # name: (defines, force_path)
-    "tile_8x4": (["RFX_TILE_W=8u"], 1),
-    "tile_4x8": (["RFX_TILE_W=4u"], 1),
-    "tile_16x2": (["RFX_TILE_W=16u"], 1),
-    "tile_32x1": (["RFX_TILE_W=32u"], 1),
-    "tile_2x16": (["RFX_TILE_W=2u"], 1),
+    "base_t128_mb7": ([], 1),
+    "mb8": (["RFX_SMALL_MINBLOCKS=8"], 1),
+    "pairs_mb7": (["RFX_SPHERE_PAIRS=1"], 1),
+    "pairs_mb6": (["RFX_SPHERE_PAIRS=1", "RFX_SMALL_MINBLOCKS=6"], 1),
+    "t64_mb14": (["RFX_SMALL_THREADS=64", "RFX_SMALL_MINBLOCKS=14"], 1),
+    "t96_mb9": (["RFX_SMALL_THREADS=96", "RFX_SMALL_MINBLOCKS=9"], 1),
 }
 
 
 def build():
     from reflaxman_b200 import build as B
     os.makedirs(VDIR, exist_ok=True)
-    for name, (defs, _) in VARIANTS.items():
+    built = {}
+    for name, (defs, *_) in VARIANTS.items():
         out = os.path.join(VDIR, name + ".so")
-        B.build(force=True, defines=defs, out=out)
+        key = tuple(defs)
+        if key in built:
+            if os.path.lexists(out):
+                os.remove(out)
+            os.symlink(os.path.basename(built[key]), out)   # same binary, different runtime knobs
+        else:
+            B.build(force=True, defines=defs, out=out)
+            built[key] = out
         print("built", name)
 
 
