@@ -31,7 +31,7 @@ namespace rfx
 #endif
 #define RFX_TILE_H (32u / RFX_TILE_W)
 #ifndef RFX_SPHERE_PAIRS
-#define RFX_SPHERE_PAIRS 0
+#define RFX_SPHERE_PAIRS 1
 #endif
 #ifndef RFX_SMALL_THREADS
 #define RFX_SMALL_THREADS 128

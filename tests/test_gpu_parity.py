@@ -169,3 +169,71 @@ def test_bvh_equals_brute_force(capi, oracle, n_side, size, depth):
         o.render(cam, depth, want_sig=True)
         assert np.array_equal(out[1][0][k][2], o.sig)
         cases.assert_parity(out[1][0][k][1], o.resolve()[1], "bvh frame %d" % k)
+
+
+def _mixed_scene():
+    """Everything the state machine has to get right at once: three lights (one near the scene, one behind most surfaces,
+    one with zero power), nine spheres (an odd count: the pairwise sphere loop has a remainder), a vertical wall, a plane
+    (unreachable through the reference's Scene but part of the C ABI), textured floor and skybox."""
+    s = S.default_scene(skybox=S.synthetic_texture(256, 192, 5), floor=S.synthetic_texture(64, 64, 9))
+    s["objects"].insert(3, ("sphere", (3.0, 0.8, 2.5), 0.8, S.MT_DIELECTRIC, (0.9, 0.3, 0.3), 0.6, 0.0))
+    s["objects"].append(("tri", (-6.0, 0.0, 5.0, -6.0, 4.0, 5.0, 6.0, 0.0, 5.0), S.MT_METAL, (0.8, 0.8, 1.0), 0.7, 0.0, -1,
+                         (0.0, 0.0, 0.0, 1.0, 1.0, 0.0)))
+    s["objects"].append(("plane", (0.0, 0.0, 9.0), (0.0, 0.0, -1.0), S.MT_DIELECTRIC, (0.4, 0.5, 0.4), 0.3, 0.0))
+    s["lights"].append(((2.0, 6.0, -4.0), 0.5, (1.0, 0.6, 0.4), 0.4))            # inside the scene's bounding box
+    s["lights"].append(((-5.0e9, -3.0e9, 1.0e9), 2.0e8, (0.3, 0.3, 1.0), 0.3))   # below the floor: faces almost nothing
+    s["lights"].append(((0.0, 9.0e9, 0.0), 1.0e8, (1.0, 1.0, 1.0), 0.0))         # zero power: shadow rays are still cast
+    return s
+
+
+def test_mixed_scene_all_kernels_match_oracle(capi, oracle):
+    """fast kernel (ARGB batch path), general constant-bank kernel and shared-memory kernel on a scene with several lights
+    and every object kind: identical hit paths and ray counts to the oracle, identical images to each other."""
+    W, H, refl, seed = 250, 131, 12, 4242
+    cam = S.orbit_cameras(7)[2]
+    scene = _mixed_scene()
+    o = oracle.OracleRender(scene, W, H, seed=seed).render(cam, refl, want_sig=True)
+    _, oargb = o.resolve()
+    images = {}
+    for path in (1, 2):
+        c = capi.Context(0)
+        try:
+            c.load_scene(scene); c.set_seeds(seed, seed); c.set_image_size(W, H)
+            c.force_path(path)
+            c.enable_signatures(True)
+            c.stats_reset()
+            c.render(cam, refl)
+            images[path] = c.read_argb()
+            assert np.array_equal(c.read_signatures(), o.sig), "kernel %d: hit paths differ" % path
+            st = c.stats()
+            assert st["rays"] == o.counters["rays"] and st["bounces"] == o.counters["bounces"], path
+            cases.assert_parity(images[path], oargb, "mixed scene, kernel %d" % path)
+        finally:
+            c.close()
+    assert np.array_equal(images[1], images[2])
+    c = capi.Context(0)
+    try:
+        c.load_scene(scene); c.set_seeds(seed, seed); c.set_image_size(W, H)
+        c.stats_reset()
+        fast = c.render_frames([cam], refl)[0]          # ARGB-only batch path -> k_trace_small (2-D grid fast kernel)
+        assert np.array_equal(fast, images[1])
+        assert c.stats()["rays"] == o.counters["rays"]
+    finally:
+        c.close()
+
+
+def test_fast_kernel_equals_general_kernel_full_size(capi):
+    """config 2 size: the division-free fast kernel and the general kernel produce the same 1920x1080 frame bit for bit."""
+    W, H = 1920, 1080
+    cam = S.default_camera()
+    a = capi.Context(0)
+    b = capi.Context(0)
+    try:
+        for c in (a, b):
+            c.load_scene(S.default_scene()); c.set_seeds(12345, 12345); c.set_image_size(W, H)
+        a.render(cam, 20)
+        got = b.render_frames([cam], 20)[0]
+        assert np.array_equal(a.read_argb(), got)
+        assert a.stats()["rays"] == b.stats()["rays"]
+    finally:
+        a.close(); b.close()
