@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 W, H, DEPTH = 1920, 1080, 20
 CENSUS_FLOP_PER_PIXEL = 1301.7          # SURVEY.md §8(d), config 2 (our own census build counts 1270.9)
+NCU_DRAM_BYTES_PER_LAUNCH = 8329216     # dram__bytes_read.sum + dram__bytes_write.sum of k_trace_small, profiles/r1_final (ncu --set full)
 RAYS_PER_FRAME_CANONICAL = 7493076      # oracle counters, config 2, seed 12345 (3.6136 rays/pixel); recomputed live when possible
 METRIC = "Mrays/s at 1920x1080, default scene, reflection depth 20 (frames/s alongside)"
 
@@ -294,9 +295,11 @@ def run_ours(args):
     flops_per_frame = CENSUS_FLOP_PER_PIXEL * W * H
     achieved = flops_per_frame / (k2_ms_per_frame * 1e-3) / 1e12
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                "traffic": None,
-                "kernel": "k_trace", "kernel_ms_per_launch": k2_ms_per_frame, "kernel_share_of_step": k2_share,
-                "note": "achieved = SURVEY census 1301.7 flop/pixel x 1920x1080 per launch / mean k_trace duration (CUDA events on its stream); "
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                "kernel": "k_trace_small", "kernel_ms_per_launch": k2_ms_per_frame, "kernel_share_of_step": k2_share,
+                "note": "bound is FP32 CUDA-core issue (neither hbm nor tensor: >= 80 flop per mandatory byte); traffic = dram__bytes_read+write of one "
+                        "launch from the ncu --set full capture in profiles/ (the 8.3 MB ARGB frame stays in the 126 MB L2 until evicted); "
+                        "achieved = SURVEY census 1301.7 flop/pixel x 1920x1080 per launch / mean k_trace_small duration (CUDA events on its stream); "
                         "peak = 2*128*SMs*sm_max_mhz (FFMA; MEASURED_PEAKS.json has no FP32 entry; microbench measured 70.4). The arithmetic "
                         "must stay un-fused for parity, so 0.5 is the ceiling: measured FMUL+FADD ceiling 35.8 TFLOP/s (profiles/microbench_r1.jsonl)",
                 "unfused_ceiling_tflops": 35.8, "frac_of_unfused_ceiling": achieved / 35.8}

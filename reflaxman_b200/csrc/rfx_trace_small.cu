@@ -40,6 +40,10 @@ namespace rfx
 #define RFX_SMALL_MINBLOCKS 7
 #endif
 
+// Scene features a kernel instantiation supports.  The lean instantiation (FEAT = 0: no planes, no texels, one light) is
+// what the reference's demo scene needs; leaving the other paths out keeps its code inside the 32 KB instruction cache.
+constexpr int F_PLANES = 1, F_TEXELS = 2, F_LIGHTS = 4, F_ALL = 7;
+
 constexpr int SM_TRI_BIT = SMALL_MAX_SPHERES;                       // object slots: spheres | triangles | planes
 constexpr int SM_PLANE_BIT = SMALL_MAX_SPHERES + SMALL_MAX_TRIS;
 
@@ -63,6 +67,7 @@ __device__ __forceinline__ void considerHit(Best & best, float dist, int slot, i
 // All objects against one ray.  `skip` is the slot the query ignores (the shadow loop's `*obj != hitObject`,
 // Scene.cpp:135; -1 = none).  anyHit: the caller only asks whether something is hit (shadow query), so a lane that has
 // found an occluder stops entering the sqrt/divide tails.
+template <int FEAT>
 __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d, int skip, bool anyHit, Best & best)
 {
   const float a = vsqlen(d);                                          // Sphere.cpp:50
@@ -88,14 +93,14 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
       DISC = B * B - a4 * c;                                                                 \
     }
 #define RFX_SPHERE_TAIL(OFF, B, DISC)                                                        \
-    if (DISC >= 0.0f && B < 0.0f && (OFF) != skipOff)                                        \
+    if (DISC >= 0.0f && B < 0.0f)                                                            \
     {                                                                                        \
       const float t = (-B - sqrtf(DISC)) / a2;                        /* Sphere.cpp:57 */    \
       if (t > RFX_VSN)                                                                       \
       {                                                                                      \
         const float fx = d.x * t, fy = d.y * t, fz = d.z * t;                                \
         const float dist = sqrtf((fx * fx + fy * fy) + fz * fz);      /* fullRay.length(), Sphere.cpp:62 */ \
-        if (dist > RFX_DELTA)                                                                \
+        if (dist > RFX_DELTA && (OFF) != skipOff)   /* the skipped sphere is the one the ray leaves (b > 0): it rarely gets here */ \
         {                                                                                    \
           considerHit(best, dist, (OFF) >> 4, *reinterpret_cast<const int *>(ordBase + 2 * (OFF)), t, 0.0f, 0.0f); \
           if (anyHit) a4 = __int_as_float(0x7FC00000);                                       \
@@ -176,7 +181,7 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
   }
 
   // ---- planes (unreachable through the reference's Scene, kept for API completeness): Plane.cpp:36-73
-  const int nP = sc.nP;
+  const int nP = (FEAT & F_PLANES) ? sc.nP : 0;
 #pragma unroll 1
   for (int k = 0; k < nP; k++)
   {
@@ -200,7 +205,7 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
 
 // ---- Scene::trace (reference Scene.cpp:73-236) ------------------------------------------------------------------------
 // `events` counts bounce-loop iterations in its low half and shadow rays in its high half (one register instead of two).
-template <bool SIG>
+template <bool SIG, int FEAT>
 __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ray, int reflNumber, V3 randDir, uint32_t & events, uint32_t & sig)
 {
   V3 mul = mk(1.0f, 1.0f, 1.0f);
@@ -222,7 +227,7 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
   {
     Best hit;
     hit.dist = FLT_MAX; hit.slot = -1; hit.order = 0x7FFFFFFF; hit.t = 0; hit.u = 0; hit.v = 0;
-    intersectSmall(sc, qo, qd, shadowQuery ? hslot : -1, shadowQuery, hit);
+    intersectSmall<FEAT>(sc, qo, qd, shadowQuery ? hslot : -1, shadowQuery, hit);
 
     if (!shadowQuery)
     {
@@ -233,7 +238,7 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
         if (SIG) RFX_SIG(sig, 0xFFFF);
         float u, v;
         skyDirToUv(qd, sc.halfTileW, sc.halfTileH, u, v);
-        const V3 sky = texSampleRef(sc.skyTex >= 0 ? &sc.tex[sc.skyTex] : nullptr, sc.byteLut, u, v);
+        const V3 sky = texSampleRef((FEAT & F_TEXELS) && sc.skyTex >= 0 ? &sc.tex[sc.skyTex] : nullptr, sc.byteLut, u, v);
         pix = mk(clamp01(pix.x + (mul.x * sky.x) * sc.env[0]), clamp01(pix.y + (mul.y * sky.y) * sc.env[1]),
                  clamp01(pix.z + (mul.z * sky.z) * sc.env[2]));            // Scene.cpp:230-231
         break;
@@ -261,10 +266,10 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
           // tuvTrans * Vector3(u, v, 0): (u*_11 + v*_12) + 0*_13 with _13 == 0, Triangle.cpp:91
           const float tx = (hit.u * tr.tuv[0] + hit.v * tr.tuv[1]) + 0.0f;
           const float ty = (hit.u * tr.tuv[2] + hit.v * tr.tuv[3]) + 0.0f;
-          color = texSampleRef(&sc.tex[tex], sc.byteLut, tr.tu0 + tx, tr.tv0 + ty);
+          color = texSampleRef((FEAT & F_TEXELS) ? &sc.tex[tex] : nullptr, sc.byteLut, tr.tu0 + tx, tr.tv0 + ty);
         }
       }
-      else
+      else if (FEAT & F_PLANES)
       {
         const Plane & pl = sc.pl[hit.slot - SM_PLANE_BIT];
         norm = mk(pl.n[0], pl.n[1], pl.n[2]);
@@ -327,7 +332,8 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
 
     // ---- next light that faces the surface gets a shadow query, Scene.cpp:118-129
     bool cast = false;
-    for (; li < sc.nL; li++)
+    const int nL = (FEAT & F_LIGHTS) ? sc.nL : (sc.nL > 0 ? 1 : 0);
+    for (; li < nL; li++)
     {
       const Light & L = sc.light[li];
       const V3 toLight = mk(L.ox - qo.x, L.oy - qo.y, L.oz - qo.z);
@@ -385,6 +391,7 @@ __device__ __forceinline__ void flushCounters(unsigned long long * __restrict__ 
 
 // Fast kernel: a row-aligned slice (whole frame, band of rows, or this GPU's strips of a split frame), one sample per
 // pixel, no jitter, ARGB output only.  2-D grid: blockIdx.y = tile row, blockIdx.x * warps + warp = tile column.
+template <int FEAT>
 __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_small(const __grid_constant__ SmallScene sc, const __grid_constant__ FrameParams fp,
                                                                const uint32_t * __restrict__ sampleStates, uint32_t * __restrict__ argbOut,
                                                                unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1)
@@ -412,7 +419,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
     V3 rd;
     rngTriple(s, rd.x, rd.y, rd.z);
     uint32_t sig = 0;
-    const V3 c = traceSmall<false>(sc, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, events, sig);
+    const V3 c = traceSmall<false, FEAT>(sc, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, events, sig);
     argbOut[q] = packArgb(c.x, c.y, c.z);
   }
   flushCounters(counters, events & 0xFFFFu, events >> 16, (blockIdx.y * gridDim.x + blockIdx.x) * (SMALL_THREADS / 32) + warp);
@@ -505,7 +512,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
                         (px * fp.view[3] + py * fp.view[4]) + fp.rz * fp.view[5],
                         (px * fp.view[6] + py * fp.view[7]) + fp.rz * fp.view[8]);
       uint32_t events = 0;
-      const V3 c = traceSmall<true>(sc, eye, ray, fp.reflNum, rd, events, sig);
+      const V3 c = traceSmall<true, F_ALL>(sc, eye, ray, fp.reflNum, rd, events, sig);
       nBounces += events & 0xFFFFu; nShadow += events >> 16;
       fin = blockMode ? c : vadd(fin, c);
       if (++ssy == sn) { ssy = 0; ssx++; }                  // ssx outer, ssy inner: the reference's summation order
@@ -561,7 +568,19 @@ int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st
       {
         const uint32_t tilesX = (fp.W + RFX_TILE_W - 1) / RFX_TILE_W, warps = SMALL_THREADS / 32;
         const dim3 grid((tilesX + warps - 1) / warps, (uint32_t)((rows + RFX_TILE_H - 1) / RFX_TILE_H));
-        k_trace_small<<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W));
+        // scene features decide the instantiation: texel-free, plane-free, single-light scenes run the lean one
+        bool texels = false;
+        for (int i = 0; i < SMALL_MAX_TEX; i++) texels = texels || sc.tex[i].px != nullptr;
+        const bool lean = !texels && sc.nP == 0 && sc.nL <= 1;
+#ifdef RFX_NO_LEAN
+        const bool useLean = false;
+#else
+        const bool useLean = lean;
+#endif
+        if (useLean)
+          k_trace_small<0><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W));
+        else
+          k_trace_small<F_ALL><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W));
         return 1;
       }
       nThreads = (uint64_t)((fp.W + RFX_TILE_W - 1) / RFX_TILE_W) * ((rows + RFX_TILE_H - 1) / RFX_TILE_H) * 32;

@@ -11,12 +11,8 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 
 VARIANTS = {
     # name: (defines, force_path)
-    "base_t128_mb7": ([], 1),
-    "mb8": (["RFX_SMALL_MINBLOCKS=8"], 1),
-    "pairs_mb7": (["RFX_SPHERE_PAIRS=1"], 1),
-    "pairs_mb6": (["RFX_SPHERE_PAIRS=1", "RFX_SMALL_MINBLOCKS=6"], 1),
-    "t64_mb14": (["RFX_SMALL_THREADS=64", "RFX_SMALL_MINBLOCKS=14"], 1),
-    "t96_mb9": (["RFX_SMALL_THREADS=96", "RFX_SMALL_MINBLOCKS=9"], 1),
+    "lean": ([], 1),
+    "full": (["RFX_NO_LEAN=1"], 1),
 }
 
 
