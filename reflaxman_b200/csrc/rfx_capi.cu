@@ -739,12 +739,14 @@ int rfx_skip_samples(rfx_ctx * ctx, uint64_t n)
   if (!ctx) return RFX_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   int rc;
-  if ((rc = useStream(ctx, ctx->stream)) != RFX_OK) return rc;
+  // the stream state lives on the device and advances in stream order: stay on the stream the renders use
+  cudaStream_t st = ctx->lastStream ? ctx->lastStream : ctx->stream;
+  if ((rc = useStream(ctx, st)) != RFX_OK) return rc;
   const uint64_t chunk = 1ull << 28;
   while (n > 0)
   {
     const uint64_t m = std::min(n, chunk);
-    if ((rc = rankSamples(ctx, m, true, ctx->stream)) != RFX_OK) return rc;
+    if ((rc = rankSamples(ctx, m, true, st)) != RFX_OK) return rc;
     n -= m;
   }
   return RFX_OK;
