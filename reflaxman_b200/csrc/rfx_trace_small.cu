@@ -136,8 +136,8 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
 #undef RFX_SPHERE_TAIL
 
   // ---- triangles: third row of axTrans*(origin - v0) and axTrans*ray (Triangle.cpp:56-57, Matrix33.cpp:232-234);
-  // t = -oz/rz > 2^-63 needs |rz| > 2^-63 and oz, rz of opposite sign (the sign of an IEEE quotient is exact; a zero oz
-  // gives t = 0 and fails in the tail), so everything else is skipped without dividing.  A closed lane (any-hit query
+  // t = -oz/rz > 2^-63 needs |rz| > 2^-63 and oz, rz nonzero of opposite sign (the sign of an IEEE quotient is exact), so
+  // everything else is skipped without dividing.  A closed lane (any-hit query
   // that has its occluder) carries +inf as the |rz| threshold.
   float rzMin = (anyHit && best.slot >= 0) ? __int_as_float(0x7F800000) : RFX_VSN;
   const char * triBase = reinterpret_cast<const char *>(sc.triPk);
@@ -153,7 +153,9 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
     const float px = o.x - A.x, py = o.y - A.y, pz = o.z - A.z;
     const float oz = (px * A.w + py * B.x) + pz * B.y;
     const float rz = (d.x * A.w + d.y * B.x) + d.z * B.y;
-    if ((__float_as_int(oz) ^ __float_as_int(rz)) < 0 && fabsf(rz) > rzMin && off != skipTri)
+    // (a zero oz — a ray that starts exactly on the plane, common for rays leaving a floor triangle towards its coplanar
+    // neighbour — would give t = 0 and fail in the tail, but 0 / rz takes div.rn's 30-instruction slow path: reject it here)
+    if ((__float_as_int(oz) ^ __float_as_int(rz)) < 0 && fabsf(rz) > rzMin && fabsf(oz) > 0.0f && off != skipTri)
     {
       const float t = -oz / rz;                                       // Triangle.cpp:61
       if (t > RFX_VSN)

@@ -11,8 +11,7 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 
 VARIANTS = {
     # name: (defines, force_path)
-    "lean": ([], 1),
-    "full": (["RFX_NO_LEAN=1"], 1),
+    "base": ([], 1),
 }
 
 
