@@ -30,8 +30,8 @@ namespace rfx
 #define RFX_TILE_W 4u      // pixel tile of one warp: RFX_TILE_W x RFX_TILE_H = 32 (4x8 measured best, profiles/variants_d_r1.jsonl)
 #endif
 #define RFX_TILE_H (32u / RFX_TILE_W)
-#ifndef RFX_SPHERE_PAIRS
-#define RFX_SPHERE_PAIRS 1
+#ifndef RFX_SPHERE_GROUP
+#define RFX_SPHERE_GROUP 4     // spheres per loop trip: 1, 2 or 4 (profiles/README.md)
 #endif
 #ifndef RFX_SMALL_THREADS
 #define RFX_SMALL_THREADS 128
@@ -92,8 +92,8 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
       const float c = ((vx * vx + vy * vy) + vz * vz) - S.w;                                 \
       DISC = B * B - a4 * c;                                                                 \
     }
+#define RFX_SPHERE_GATE(B, DISC) ((DISC) >= 0.0f && (B) < 0.0f)
 #define RFX_SPHERE_TAIL(OFF, B, DISC)                                                        \
-    if (DISC >= 0.0f && B < 0.0f)                                                            \
     {                                                                                        \
       const float t = (-B - sqrtf(DISC)) / a2;                        /* Sphere.cpp:57 */    \
       if (t > RFX_VSN)                                                                       \
@@ -109,10 +109,31 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
     }
   const int endOff = sc.nS << 4;
   int off = 0;
-#if RFX_SPHERE_PAIRS
-  // two spheres per trip: the two reject chains are independent (ILP for a scheduler with ~6 resident warps) and share the
-  // loop bookkeeping; the second sphere's discriminant is evaluated before the first tail, so an any-hit lane that closes in
-  // the first tail re-poisons it explicitly
+  // Several spheres per trip: their reject chains are independent (ILP for a scheduler that holds ~7 warps), they share the
+  // loop bookkeeping, and ONE divergent region gates all their tails (the common case — no lane passes any gate — costs one
+  // branch).  The discriminants of a trip are evaluated before its tails, so an any-hit lane that closes in an earlier tail
+  // (a4 becomes NaN) must not enter a later one.
+#if RFX_SPHERE_GROUP == 4
+  const int endQuad = endOff & ~63;
+#pragma unroll 1
+  for (; off != endQuad; off += 64)
+  {
+    asm volatile("" : "+r"(off));
+    RFX_SPHERE_REJECT(off, s0, b0, disc0)
+    RFX_SPHERE_REJECT(off + 16, s1, b1, disc1)
+    RFX_SPHERE_REJECT(off + 32, s2, b2, disc2)
+    RFX_SPHERE_REJECT(off + 48, s3, b3, disc3)
+    const bool g0 = RFX_SPHERE_GATE(b0, disc0), g1 = RFX_SPHERE_GATE(b1, disc1), g2 = RFX_SPHERE_GATE(b2, disc2), g3 = RFX_SPHERE_GATE(b3, disc3);
+    if (g0 || g1 || g2 || g3)
+    {
+      if (g0) RFX_SPHERE_TAIL(off, b0, disc0)
+      if (g1 && a4 == a4) RFX_SPHERE_TAIL(off + 16, b1, disc1)
+      if (g2 && a4 == a4) RFX_SPHERE_TAIL(off + 32, b2, disc2)
+      if (g3 && a4 == a4) RFX_SPHERE_TAIL(off + 48, b3, disc3)
+    }
+  }
+#endif
+#if RFX_SPHERE_GROUP >= 2
   const int endPair = endOff & ~31;
 #pragma unroll 1
   for (; off != endPair; off += 32)
@@ -120,9 +141,12 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
     asm volatile("" : "+r"(off));
     RFX_SPHERE_REJECT(off, s0, b0, disc0)
     RFX_SPHERE_REJECT(off + 16, s1, b1, disc1)
-    RFX_SPHERE_TAIL(off, b0, disc0)
-    if (a4 != a4) disc1 = a4;
-    RFX_SPHERE_TAIL(off + 16, b1, disc1)
+    const bool g0 = RFX_SPHERE_GATE(b0, disc0), g1 = RFX_SPHERE_GATE(b1, disc1);
+    if (g0 || g1)
+    {
+      if (g0) RFX_SPHERE_TAIL(off, b0, disc0)
+      if (g1 && a4 == a4) RFX_SPHERE_TAIL(off + 16, b1, disc1)
+    }
   }
 #endif
 #pragma unroll 1
@@ -130,8 +154,9 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
   {
     asm volatile("" : "+r"(off));   // keeps `off` the only induction variable (ptxas otherwise strength-reduces it into five)
     RFX_SPHERE_REJECT(off, s0, b0, disc0)
-    RFX_SPHERE_TAIL(off, b0, disc0)
+    if (RFX_SPHERE_GATE(b0, disc0)) RFX_SPHERE_TAIL(off, b0, disc0)
   }
+#undef RFX_SPHERE_GATE
 #undef RFX_SPHERE_REJECT
 #undef RFX_SPHERE_TAIL
 
@@ -144,43 +169,51 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
   const char * triOrd = reinterpret_cast<const char *>(&sc.mat[SM_TRI_BIT].order);
   const int skipTri = (skip - SM_TRI_BIT) * 48;
   const int endTri = sc.nT * 48;
-#pragma unroll 1
-  for (int off = 0; off != endTri; off += 48)
-  {
-    asm volatile("" : "+r"(off));
-    const float4 A = *reinterpret_cast<const float4 *>(triBase + off);
-    const float4 B = *reinterpret_cast<const float4 *>(triBase + off + 16);
-    const float px = o.x - A.x, py = o.y - A.y, pz = o.z - A.z;
-    const float oz = (px * A.w + py * B.x) + pz * B.y;
-    const float rz = (d.x * A.w + d.y * B.x) + d.z * B.y;
-    // (a zero oz — a ray that starts exactly on the plane, common for rays leaving a floor triangle towards its coplanar
-    // neighbour — would give t = 0 and fail in the tail, but 0 / rz takes div.rn's 30-instruction slow path: reject it here)
-    if ((__float_as_int(oz) ^ __float_as_int(rz)) < 0 && fabsf(rz) > rzMin && fabsf(oz) > 0.0f && off != skipTri)
-    {
-      const float t = -oz / rz;                                       // Triangle.cpp:61
-      if (t > RFX_VSN)
-      {
-        const float4 C = *reinterpret_cast<const float4 *>(triBase + off + 32);
-        const float ox = (px * B.z + py * B.w) + pz * C.x;
-        const float rx = (d.x * B.z + d.y * B.w) + d.z * C.x;
-        const float oy = (px * C.y + py * C.z) + pz * C.w;
-        const float ry = (d.x * C.y + d.y * C.z) + d.z * C.w;
-        const float u = ox + t * rx;                                  // Triangle.cpp:65-66
-        const float v = oy + t * ry;
-        if (u >= 0.0f && v >= 0.0f && u + v < 1.0f)
-        {
-          const float fx = d.x * t, fy = d.y * t, fz = d.z * t;
-          const float sq = (fx * fx + fy * fy) + fz * fz;
-          if (sq > RFX_DELTA * RFX_DELTA)
-          {
-            const int k = off / 48;
-            considerHit(best, sqrtf(sq), SM_TRI_BIT + k, *reinterpret_cast<const int *>(triOrd + k * 32), t, u, v);
-            if (anyHit) rzMin = __int_as_float(0x7F800000);
-          }
-        }
-      }
+  // (a zero oz — a ray that starts exactly on the plane, common for rays leaving a floor triangle towards its coplanar
+  // neighbour — would give t = 0 and fail in the tail, but 0 / rz takes div.rn's 30-instruction slow path: the gate rejects it)
+#define RFX_TRI_REJECT(OFF, A, B, PX, PY, PZ, OZ, RZ)                                         \
+    const float4 A = *reinterpret_cast<const float4 *>(triBase + (OFF));                      \
+    const float4 B = *reinterpret_cast<const float4 *>(triBase + (OFF) + 16);                 \
+    const float PX = o.x - A.x, PY = o.y - A.y, PZ = o.z - A.z;                               \
+    const float OZ = (PX * A.w + PY * B.x) + PZ * B.y;                                        \
+    const float RZ = (d.x * A.w + d.y * B.x) + d.z * B.y;
+#define RFX_TRI_GATE(OFF, OZ, RZ) ((__float_as_int(OZ) ^ __float_as_int(RZ)) < 0 && fabsf(RZ) > rzMin && fabsf(OZ) > 0.0f && (OFF) != skipTri)
+#define RFX_TRI_TAIL(OFF, B, PX, PY, PZ, OZ, RZ)                                              \
+    {                                                                                         \
+      const float t = -OZ / RZ;                                       /* Triangle.cpp:61 */   \
+      if (t > RFX_VSN)                                                                        \
+      {                                                                                       \
+        const float4 C = *reinterpret_cast<const float4 *>(triBase + (OFF) + 32);             \
+        const float ox = (PX * B.z + PY * B.w) + PZ * C.x;                                    \
+        const float rx = (d.x * B.z + d.y * B.w) + d.z * C.x;                                 \
+        const float oy = (PX * C.y + PY * C.z) + PZ * C.w;                                    \
+        const float ry = (d.x * C.y + d.y * C.z) + d.z * C.w;                                 \
+        const float u = ox + t * rx;                                  /* Triangle.cpp:65-66 */ \
+        const float v = oy + t * ry;                                                          \
+        if (u >= 0.0f && v >= 0.0f && u + v < 1.0f)                                           \
+        {                                                                                     \
+          const float fx = d.x * t, fy = d.y * t, fz = d.z * t;                               \
+          const float sq = (fx * fx + fy * fy) + fz * fz;                                     \
+          if (sq > RFX_DELTA * RFX_DELTA)                                                     \
+          {                                                                                   \
+            const int k = (OFF) / 48;                                                         \
+            considerHit(best, sqrtf(sq), SM_TRI_BIT + k, *reinterpret_cast<const int *>(triOrd + k * 32), t, u, v); \
+            if (anyHit) rzMin = __int_as_float(0x7F800000);                                   \
+          }                                                                                   \
+        }                                                                                     \
+      }                                                                                       \
     }
+  int toff = 0;
+#pragma unroll 1
+  for (; toff != endTri; toff += 48)
+  {
+    asm volatile("" : "+r"(toff));
+    RFX_TRI_REJECT(toff, A0, B0, px0, py0, pz0, oz0, rz0)
+    if (RFX_TRI_GATE(toff, oz0, rz0)) RFX_TRI_TAIL(toff, B0, px0, py0, pz0, oz0, rz0)
   }
+#undef RFX_TRI_REJECT
+#undef RFX_TRI_GATE
+#undef RFX_TRI_TAIL
 
   // ---- planes (unreachable through the reference's Scene, kept for API completeness): Plane.cpp:36-73
   const int nP = (FEAT & F_PLANES) ? sc.nP : 0;
