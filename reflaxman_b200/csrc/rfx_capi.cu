@@ -515,6 +515,7 @@ int rfx_create(rfx_ctx ** out, int device)
   auto step = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
   step(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   step(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  if (initRngTables() != 0) step(cudaErrorUnknown);
   step(cudaMalloc((void **)&ctx->dRng, 2 * sizeof(uint32_t)));
   step(cudaMalloc((void **)&ctx->dStatus, sizeof(int)));
   step(cudaMalloc((void **)&ctx->dCounters, 64 * sizeof(unsigned long long)));

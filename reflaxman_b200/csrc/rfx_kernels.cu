@@ -32,12 +32,50 @@ namespace rfx
 
 uint32_t lcgJumpHost(uint32_t s, uint64_t n) { return lcgJump(s, (uint32_t)n); }
 
+// Jump-ahead tables for K1.  n draws ahead is the affine map s -> A_n s + C_n; thread t of block b starts
+// (b * RNG_TRIPLES_PER_BLOCK + t * RNG_TRIPLES_PER_THREAD) triples into the pass.  The block part is applied nibble by nibble
+// of b (6 table steps cover 2^24 blocks; the largest pass, a 2^28-sample stream skip, has 2^18), the thread part is one step: ~30 instructions instead of a 28-round binary powering.
+__constant__ uint32_t c_jumpBlock[6][16][2];   // [nibble position][nibble value] -> (A, C) of (value << 4*pos) * 3 * RNG_TRIPLES_PER_BLOCK draws
+__device__ uint2 g_jumpThread[RNG_THREADS];    // t -> (A, C) of t * 3 * RNG_TRIPLES_PER_THREAD draws (global: one coalesced 8-byte load per thread;
+                                               // a per-lane index into the constant bank would serialise 32 ways)
+
+int initRngTables()
+{
+  static uint32_t blk[6][16][2], thr[RNG_THREADS][2];
+  auto affine = [](uint64_t draws, uint32_t out[2]) {
+    const uint32_t c = lcgJump(0u, (uint32_t)draws);          // f^n(0) = C_n
+    out[0] = lcgJump(1u, (uint32_t)draws) - c;                // f^n(1) - C_n = A_n
+    out[1] = c;
+  };
+  for (int pos = 0; pos < 6; pos++)
+    for (uint64_t v = 0; v < 16; v++) affine((v << (4 * pos)) * 3ull * RNG_TRIPLES_PER_BLOCK, blk[pos][v]);
+  for (uint64_t t = 0; t < RNG_THREADS; t++) affine(t * 3ull * RNG_TRIPLES_PER_THREAD, thr[t]);
+  if (cudaMemcpyToSymbol(c_jumpBlock, blk, sizeof(blk)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(g_jumpThread, thr, sizeof(thr)) != cudaSuccess) return 1;
+  return 0;
+}
+
+// LCG state at the first triple of this thread
+__device__ __forceinline__ uint32_t rngThreadStart(uint32_t s)
+{
+  uint32_t b = blockIdx.x;
+#pragma unroll
+  for (int pos = 0; pos < 6; pos++, b >>= 4)
+  {
+    if (b == 0) break;                                         // uniform
+    const uint32_t v = b & 15u;
+    s = c_jumpBlock[pos][v][0] * s + c_jumpBlock[pos][v][1];
+  }
+  const uint2 m = __ldg(&g_jumpThread[threadIdx.x]);
+  return m.x * s + m.y;
+}
+
 __global__ void __launch_bounds__(RNG_THREADS) k_rng_count(const uint32_t * __restrict__ stateIn, uint32_t * __restrict__ blockCounts,
                                                            uint8_t * __restrict__ acceptMasks)
 {
   __shared__ int warpSums[RNG_THREADS / 32];
   const uint32_t gid = blockIdx.x * RNG_THREADS + threadIdx.x;
-  uint32_t s = lcgJump(*stateIn, gid * (3u * RNG_TRIPLES_PER_THREAD));
+  uint32_t s = rngThreadStart(*stateIn);
   uint32_t mask = 0;
 #pragma unroll
   for (int k = 0; k < RNG_TRIPLES_PER_THREAD; k++)
@@ -126,7 +164,7 @@ __global__ void __launch_bounds__(RNG_THREADS) k_rng_scatter(const uint32_t * __
   }
 
   const uint32_t gid = blockIdx.x * RNG_THREADS + threadIdx.x;
-  const uint32_t sStart = lcgJump(*stateIn, gid * (3u * RNG_TRIPLES_PER_THREAD));
+  const uint32_t sStart = rngThreadStart(*stateIn);
   uint32_t s = sStart;
   const uint32_t mask = acceptMasks[gid];
   const int cnt = __popc(mask);

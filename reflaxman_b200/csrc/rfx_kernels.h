@@ -31,6 +31,8 @@ struct RngWork
   uint64_t ownPeriod = 0;
   uint32_t ownWorld = 0, ownRank = 0;
 };
+// uploads K1's jump-ahead tables to the current device (once per context); 0 = ok
+int initRngTables();
 // number of blocks that over-provisions n accepted triples (acceptance pi/6 = 0.5236)
 uint32_t rngBlocksFor(uint64_t n);
 // enqueue count + scan + scatter; returns the number of kernels launched
