@@ -214,11 +214,12 @@ __device__ __forceinline__ V3 texSampleRef(const TexRef * t, const float * __res
 // direction -> (u, v) in the 4x3 cube-cross atlas, Skybox.cpp:39-103.  Every face evaluates centre +- (p / major) * halfTile;
 // a - q*h == a + ((-p)/m)*h bit for bit (negation commutes with IEEE division, multiplication and turns + into -), so the
 // face only selects operands and the two divisions are issued once instead of once per face.
-__device__ __forceinline__ void skyDirToUv(V3 ray, float hw, float hh, float & u, float & v)
+// rayLen = ray.length(), passed in by callers that already hold it (same operations, same value)
+__device__ __forceinline__ void skyDirToUv(V3 ray, float rayLen, float hw, float hh, float & u, float & v)
 {
   const float uLeft = 1.0f / 8.0f, vMid = 3.0f / 6.0f, uFront = 3.0f / 8.0f, uRight = 5.0f / 8.0f, uBack = 7.0f / 8.0f;
   const float vTop = 5.0f / 6.0f, vBottom = 1.0f / 6.0f;
-  const V3 n = normalizeVec(ray);
+  const V3 n = (rayLen > RFX_VSN) ? mk(ray.x / rayLen, ray.y / rayLen, ray.z / rayLen) : ray;   // trace_math.cpp:3-12
   const float x = n.x, y = n.y, z = n.z;
   const float ax = fabsf(x) + RFX_VSN, ay = fabsf(y) + RFX_VSN, az = fabsf(z) + RFX_VSN;
   float pu, pv, major, cu, cv;

@@ -255,7 +255,7 @@ __device__ __forceinline__ V3 texSample(const SceneView & sc, int texId, float u
 __device__ __forceinline__ V3 skySample(const SceneView & sc, V3 ray)
 {
   float u, v;
-  skyDirToUv(ray, sc.h->halfTileW, sc.h->halfTileH, u, v);
+  skyDirToUv(ray, vlen(ray), sc.h->halfTileW, sc.h->halfTileH, u, v);
   return texSample(sc, sc.h->skyTex, u, v);
 }
 

@@ -272,7 +272,7 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
       {
         if (SIG) RFX_SIG(sig, 0xFFFF);
         float u, v;
-        skyDirToUv(qd, sc.halfTileW, sc.halfTileH, u, v);
+        skyDirToUv(qd, vlen(qd), sc.halfTileW, sc.halfTileH, u, v);
         const V3 sky = texSampleRef((FEAT & F_TEXELS) && sc.skyTex >= 0 ? &sc.tex[sc.skyTex] : nullptr, sc.byteLut, u, v);
         pix = mk(clamp01(pix.x + (mul.x * sky.x) * sc.env[0]), clamp01(pix.y + (mul.y * sky.y) * sc.env[1]),
                  clamp01(pix.z + (mul.z * sky.z) * sc.env[2]));            // Scene.cpp:230-231
@@ -400,7 +400,9 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
     if (mul.x < 0.01f && mul.y < 0.01f && mul.z < 0.01f) break;
     if (++refl >= reflNumber) break;
 
-    qd = vadd(normalizeVec(reflect), vscale(randDir, 1.0f - mrefl));      // Scene.cpp:226
+    // reflect.normalized(): its length is the reflectLen of the hit set-up (same operands, same operations), Vector3.cpp:55-64
+    const V3 rn = (reflectLen > RFX_VSN) ? mk(reflect.x / reflectLen, reflect.y / reflectLen, reflect.z / reflectLen) : reflect;
+    qd = vadd(rn, vscale(randDir, 1.0f - mrefl));                        // Scene.cpp:226
     shadowQuery = false;
   }
   return pix;

@@ -11,9 +11,7 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 
 VARIANTS = {
     # name: (defines, force_path)
-    "sph4_tri1": ([], 1),
-    "sph4_tri2": (["RFX_TRI_GROUP=2"], 1),
-    "sph4_tri2_mb6": (["RFX_TRI_GROUP=2", "RFX_SMALL_MINBLOCKS=6"], 1),
+    "base": ([], 1),
 }
 
 
