@@ -11,7 +11,9 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 
 VARIANTS = {
     # name: (defines, force_path)
-    "base": ([], 1),
+    "scalar": ([], 1),
+    "packed": (["RFX_SPHERE_PACKED=1"], 1),
+    "packed_mb6": (["RFX_SPHERE_PACKED=1", "RFX_SMALL_MINBLOCKS=6"], 1),
 }
 
 
