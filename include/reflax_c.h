@@ -158,7 +158,10 @@ RFX_API int rfx_enable_profiling(rfx_ctx * ctx, int on);
 RFX_API int rfx_force_path(rfx_ctx * ctx, int path);
 /* acceleration structure of the shared-memory kernel: 0 = automatic (bounding-volume hierarchy over the spheres when there are
  * more than 32), 1 = always, 2 = never (the reference's brute-force list walk).  Results are identical; tests compare them. */
-RFX_API int rfx_set_bvh_mode(rfx_ctx * ctx, int mode);       /* bracket every K2 launch with CUDA events (bench roofline) */
+RFX_API int rfx_set_bvh_mode(rfx_ctx * ctx, int mode);
+/* cost-ordered tile scheduling of the constant-bank fast kernel: every launch records which tiles held long paths and the next
+ * launch over the same image starts those first (1 = on, the default; 0 = always index order).  Results are identical. */
+RFX_API int rfx_set_tile_ordering(rfx_ctx * ctx, int on);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,7 @@ SYMBOLS = [
     ("rfx_enable_profiling", C.c_int, [C.c_void_p, C.c_int]),
     ("rfx_force_path", C.c_int, [C.c_void_p, C.c_int]),
     ("rfx_set_bvh_mode", C.c_int, [C.c_void_p, C.c_int]),
+    ("rfx_set_tile_ordering", C.c_int, [C.c_void_p, C.c_int]),
 ]
 
 _lib = None
@@ -326,6 +327,9 @@ class Context:
 
     def set_bvh_mode(self, mode):
         self._ck(self.L.rfx_set_bvh_mode(self.h, mode), "rfx_set_bvh_mode")
+
+    def set_tile_ordering(self, on=True):
+        self._ck(self.L.rfx_set_tile_ordering(self.h, 1 if on else 0), "rfx_set_tile_ordering")
 
     def device_info(self):
         d = RfxDeviceInfo()

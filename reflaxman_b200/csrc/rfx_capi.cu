@@ -126,6 +126,13 @@ struct rfx_ctx
   // ---- device scene
   unsigned char * dBlob = nullptr; size_t blobCap = 0; uint32_t blobBytes = 0;
   SmallScene small; bool smallOk = false;   // constant-bank form of the same scene, when it fits
+  // cost-ordered tile scheduling of the fast kernel (TileOrder, rfx_kernels.h): two list sets, used alternately
+  uint32_t * dTileLists[2] = { nullptr, nullptr }; size_t tileListCap[2] = { 0, 0 };
+  uint32_t * dTileCounts = nullptr;         // [2][TILE_CLASSES]
+  int tileSlot = 0;                         // set the NEXT launch records into
+  bool tileHistory = false;                 // the other set holds the order recorded by the previous launch ...
+  uint64_t tileKey[4] = { 0, 0, 0, 0 };     // ... over this grid (image size, row range, strip split)
+  bool tileOrdering = true;
   int forcePath = 0;                        // 0 auto, 1 small (constant bank), 2 big (shared memory) — tests exercise both
   float * dLut = nullptr;
   float4 * dBvhNodes = nullptr; size_t bvhNodesCap = 0;   // big scenes only (see buildBvh)
@@ -414,6 +421,34 @@ int rankSamples(rfx_ctx * ctx, uint64_t n, bool skipOnly, cudaStream_t st, uint6
 
 const uint64_t MAX_CALLS_PER_LAUNCH = 1ull << 25;   // bounds the ranked-state scratch (128 MB) for huge SSAA factors / 8K frames
 
+// Fills w.order for a fast-kernel launch and remembers what the launch will have recorded (see TileOrder).  History is
+// only reused by a launch over exactly the same grid; any other launch of the fast kernel starts a new history.
+int armTileOrder(rfx_ctx * ctx, TraceWork & w, cudaStream_t st)
+{
+  w.order = TileOrder();
+  const uint32_t grid = ctx->smallOk && ctx->forcePath != 2 ? fastGridSize(w) : 0;
+  if (!ctx->tileOrdering || grid == 0 || grid > (1u << 22)) { ctx->tileHistory = false; return RFX_OK; }
+  const uint64_t key[4] = { ((uint64_t)w.fp.W << 32) | w.fp.H, w.fp.p0, w.fp.p1,
+                            ((uint64_t)w.fp.stripRows << 40) | ((uint64_t)w.fp.stripWorld << 20) | w.fp.stripRank };
+  int rc;
+  const int out = ctx->tileSlot, in = out ^ 1;
+  if ((rc = ensure(ctx, ctx->dTileLists[out], ctx->tileListCap[out], (size_t)grid * TILE_CLASSES)) != RFX_OK) return rc;
+  if (!ctx->dTileCounts) CK(cudaMalloc((void **)&ctx->dTileCounts, 2 * TILE_CLASSES * sizeof(uint32_t)));
+  CK(cudaMemsetAsync(ctx->dTileCounts + out * TILE_CLASSES, 0, TILE_CLASSES * sizeof(uint32_t), st));
+  w.order.outLists = ctx->dTileLists[out];
+  w.order.outCounts = ctx->dTileCounts + out * TILE_CLASSES;
+  w.order.capacity = grid;
+  if (ctx->tileHistory && memcmp(key, ctx->tileKey, sizeof(key)) == 0 && ctx->tileListCap[in] >= (size_t)grid * TILE_CLASSES)
+  {
+    w.order.inLists = ctx->dTileLists[in];
+    w.order.inCounts = ctx->dTileCounts + in * TILE_CLASSES;
+  }
+  memcpy(ctx->tileKey, key, sizeof(key));
+  ctx->tileHistory = true;
+  ctx->tileSlot = in;
+  return RFX_OK;
+}
+
 // render pixels [p0, p1) of the frame latched by render_begin
 // preStates: random states already ranked for exactly [p0, p1) (batch path ranks several frames per K1 pass); NULL = rank here
 int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, bool writeImage, cudaStream_t st,
@@ -463,6 +498,7 @@ int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, boo
         CK(cudaEventRecord(evA, st));
       }
       const bool useSmall = ctx->forcePath == 1 ? ctx->smallOk : ctx->forcePath == 2 ? false : ctx->smallOk;
+      if (useSmall && (rc = armTileOrder(ctx, w, st)) != RFX_OK) return rc;
       ctx->stats.kernel_launches += useSmall ? launchTraceSmall(ctx->small, w, st) : launchTrace(w, st);
       if (evB) CK(cudaEventRecord(evB, st));
       CK(cudaGetLastError());
@@ -553,7 +589,7 @@ void rfx_destroy(rfx_ctx * ctx)
   for (HostTex & t : ctx->tex) if (t.dev) cudaFree(t.dev);
   cudaFree(ctx->dBlob); cudaFree(ctx->dLut); cudaFree(ctx->dImage); cudaFree(ctx->dSig); cudaFree(ctx->dRng);
   cudaFree(ctx->dBlockCounts); cudaFree(ctx->dBlockOffsets); cudaFree(ctx->dSampleStates); cudaFree(ctx->dStatus);
-  cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dAcceptMasks); cudaFree(ctx->dBvhNodes); cudaFree(ctx->dBvhPrims);
+  cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dAcceptMasks); cudaFree(ctx->dBvhNodes); cudaFree(ctx->dBvhPrims); cudaFree(ctx->dTileLists[0]); cudaFree(ctx->dTileLists[1]); cudaFree(ctx->dTileCounts);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   for (int i = 0; i < 3; i++)
   {
@@ -903,6 +939,7 @@ int rfx_render_strips(rfx_ctx * ctx, uint32_t strip_rows, uint32_t world, uint32
     evA = ctx->evPool[ctx->evUsed++]; evB = ctx->evPool[ctx->evUsed++];
     CK(cudaEventRecord(evA, st));
   }
+  if ((rc = armTileOrder(ctx, w, st)) != RFX_OK) return rc;
   ctx->stats.kernel_launches += launchTraceSmall(ctx->small, w, st);
   if (evB) CK(cudaEventRecord(evB, st));
   CK(cudaGetLastError());
@@ -1251,6 +1288,14 @@ int rfx_force_path(rfx_ctx * ctx, int path)
 {
   if (!ctx || path < 0 || path > 2) return RFX_ERR_ARG;
   ctx->forcePath = path;
+  return RFX_OK;
+}
+
+int rfx_set_tile_ordering(rfx_ctx * ctx, int on)
+{
+  if (!ctx) return RFX_ERR_ARG;
+  ctx->tileOrdering = on != 0;
+  ctx->tileHistory = false;
   return RFX_OK;
 }
 

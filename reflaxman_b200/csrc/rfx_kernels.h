@@ -39,6 +39,21 @@ uint32_t rngBlocksFor(uint64_t n);
 int launchRngRank(const RngWork & w, cudaStream_t st);
 
 // ---- K2: trace + shade ----------------------------------------------------------------------------------------
+// Cost-ordered tile scheduling of the fast kernel.  Path lengths differ by 20x between tiles (sky: one segment; between two
+// mirror spheres: the full reflection depth), and the hardware starts CTAs in index order, so the long tiles of the image
+// centre start late and the GPU drains for ~17 % of the kernel while they finish.  Every CTA therefore files itself, at its
+// end, into one of four cost classes (longest path among its pixels); the next launch over the same grid starts the
+// expensive classes first.  Results do not depend on the order; the first launch over a grid runs in index order.
+constexpr int TILE_CLASSES = 4;
+struct TileOrder
+{
+  const uint32_t * inLists = nullptr;   // [TILE_CLASSES][capacity] packed (tileRow << 16 | tileColumnGroup); NULL = index order
+  const uint32_t * inCounts = nullptr;  // [TILE_CLASSES], sums to the grid size
+  uint32_t * outLists = nullptr;        // [TILE_CLASSES][capacity], NULL = do not record
+  uint32_t * outCounts = nullptr;       // [TILE_CLASSES], zeroed before the launch
+  uint32_t capacity = 0;
+};
+
 struct TraceWork
 {
   const void * sceneBlob;       // device scene blob (SceneHeader first)
@@ -49,9 +64,14 @@ struct TraceWork
   uint32_t * argbOut;           // optional direct ARGB target (non-additive, whole-pixel results)
   uint32_t * sigOut;            // optional per-pixel hit-path signature
   unsigned long long * counters;// device [32][2] striped {bounces, shadowRays}
+  TileOrder order;              // fast constant-bank kernel only
 };
 int launchTrace(const TraceWork & w, cudaStream_t st);                              // any scene: shared-memory resident blob
-int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st);   // small scenes: constant-bank resident
+// small scenes: constant-bank resident; *fastGrid (optional) receives the CTA count of the fast kernel's grid, 0 when the
+// general kernel ran (the caller keeps tile-order history only for fast launches)
+int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st, uint32_t * fastGrid = nullptr);
+// CTA count the fast kernel would use for this work, 0 if the work does not qualify for it
+uint32_t fastGridSize(const TraceWork & w);
 
 // Scene::trace for a list of rays (rfx_trace_rays): rays[i] uses sampleStates[i]
 int launchTraceRays(const void * sceneBlob, uint32_t sceneBytes, int n, const float * origins, const float * rays, int reflNum,

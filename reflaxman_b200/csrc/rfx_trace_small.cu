@@ -33,6 +33,10 @@ namespace rfx
 #ifndef RFX_SPHERE_GROUP
 #define RFX_SPHERE_GROUP 4     // spheres per loop trip: 1, 2 or 4 (profiles/README.md)
 #endif
+#ifndef RFX_TILE_BOUNDS
+// cost classes of the tile scheduler: class c holds the tile groups whose longest path has >= bound[c] segments (last class: the rest)
+#define RFX_TILE_BOUNDS { 8u, 4u, 2u }
+#endif
 #ifndef RFX_SMALL_THREADS
 #define RFX_SMALL_THREADS 128
 #endif
@@ -426,16 +430,50 @@ __device__ __forceinline__ void flushCounters(unsigned long long * __restrict__ 
   }
 }
 
+#ifdef RFX_CTA_TIMES
+// debug build (tools/cta_times.py): start/end time and SM of every CTA of the last fast-kernel launch
+__device__ unsigned long long g_ctaTimes[1 << 16][3];
+extern "C" __attribute__((visibility("default"))) int rfx_debug_cta_times(unsigned long long * out, int n)
+{
+  return (int)cudaMemcpyFromSymbol(out, g_ctaTimes, sizeof(unsigned long long) * 3 * n);
+}
+__device__ __forceinline__ unsigned long long globalTimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smId() { unsigned s; asm volatile("mov.u32 %0, %smid;" : "=r"(s)); return s; }
+#endif
+
 // Fast kernel: a row-aligned slice (whole frame, band of rows, or this GPU's strips of a split frame), one sample per
 // pixel, no jitter, ARGB output only.  2-D grid: blockIdx.y = tile row, blockIdx.x * warps + warp = tile column.
 template <int FEAT>
 __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_small(const __grid_constant__ SmallScene sc, const __grid_constant__ FrameParams fp,
                                                                const uint32_t * __restrict__ sampleStates, uint32_t * __restrict__ argbOut,
-                                                               unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1)
+                                                               unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1,
+                                                               const TileOrder ord)
 {
+  // which tile group does this CTA render: index order, or the previous launch's cost order (expensive classes first)
+  uint32_t bx = blockIdx.x, by = blockIdx.y;
+  if (ord.inLists)
+  {
+    uint32_t b = blockIdx.y * gridDim.x + blockIdx.x;
+    int c = 0;
+#pragma unroll
+    for (; c < TILE_CLASSES - 1; c++)
+    {
+      const uint32_t n = ord.inCounts[c];
+      if (b < n) break;
+      b -= n;
+    }
+    if (b < ord.inCounts[c])
+    {
+      const uint32_t packed = ord.inLists[(uint32_t)c * ord.capacity + b];
+      bx = packed & 0xFFFFu; by = packed >> 16;
+    }
+  }
+#ifdef RFX_CTA_TIMES
+  const unsigned long long tStart = globalTimer();
+#endif
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t x = (blockIdx.x * (SMALL_THREADS / 32) + warp) * RFX_TILE_W + (lane % RFX_TILE_W);
-  uint32_t y = y0 + blockIdx.y * RFX_TILE_H + (lane / RFX_TILE_W);
+  const uint32_t x = (bx * (SMALL_THREADS / 32) + warp) * RFX_TILE_W + (lane % RFX_TILE_W);
+  uint32_t y = y0 + by * RFX_TILE_H + (lane / RFX_TILE_W);
   if (fp.stripWorld)
   {
     // split frame: the launch enumerates only this GPU's rows; compact row -> (own strip k, row in strip) -> frame row
@@ -459,6 +497,34 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
     const V3 c = traceSmall<false, FEAT>(sc, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, events, sig);
     argbOut[q] = packArgb(c.x, c.y, c.z);
   }
+  if (ord.outLists)
+  {
+    // file this tile group under its cost class for the next launch: the longest path (bounce-loop iterations) of its pixels
+    __shared__ uint32_t sLongest[SMALL_THREADS / 32];
+    const uint32_t longest = __reduce_max_sync(0xffffffffu, events & 0xFFFFu);
+    if (lane == 0) sLongest[warp] = longest;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      uint32_t m = 0;
+#pragma unroll
+      for (int w = 0; w < SMALL_THREADS / 32; w++) m = max(m, sLongest[w]);
+      const uint32_t bounds[TILE_CLASSES - 1] = RFX_TILE_BOUNDS;
+      uint32_t cls = 0;
+#pragma unroll
+      for (int c = 0; c < TILE_CLASSES - 1; c++) cls += m < bounds[c] ? 1u : 0u;   // bounds descend: the count of bounds above m is the class
+      const uint32_t idx = atomicAdd(&ord.outCounts[cls], 1u);
+      if (idx < ord.capacity) ord.outLists[cls * ord.capacity + idx] = (by << 16) | bx;
+    }
+  }
+#ifdef RFX_CTA_TIMES
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    const unsigned id = by * gridDim.x + bx;
+    if (id < (1u << 16)) { g_ctaTimes[id][0] = tStart; g_ctaTimes[id][1] = globalTimer(); g_ctaTimes[id][2] = smId(); }
+  }
+#endif
   flushCounters(counters, events & 0xFFFFu, events >> 16, (blockIdx.y * gridDim.x + blockIdx.x) * (SMALL_THREADS / 32) + warp);
 }
 
@@ -580,8 +646,41 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
   flushCounters(counters, nBounces, nShadow, blockIdx.x * (SMALL_THREADS / 32) + (threadIdx.x >> 5));
 }
 
-int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st)
+// rows the fast kernel enumerates for this work (0 = does not qualify): whole rows, 1 sample per pixel, ARGB only
+static uint64_t fastRows(const TraceWork & w)
 {
+  const FrameParams & fp = w.fp;
+  if (fp.sampleNum != 1 || fp.jitter || w.image || w.sigOut || !w.argbOut || fp.W == 0) return 0;
+  if (fp.p0 % fp.W != 0 || fp.p1 % fp.W != 0 || (uint64_t)fp.W * fp.H >= (1ull << 32)) return 0;
+  uint64_t rows = (fp.p1 - fp.p0) / fp.W;
+  if (fp.stripWorld)
+  {
+    // rows owned by this rank: full strips plus the (possibly shorter) last strip, rounded up to whole strips
+    const uint64_t nStrips = (rows + fp.stripRows - 1) / fp.stripRows;
+    const uint64_t mine = nStrips > fp.stripRank ? (nStrips - fp.stripRank + fp.stripWorld - 1) / fp.stripWorld : 0;
+    rows = mine * fp.stripRows;
+  }
+  if ((rows + RFX_TILE_H - 1) / RFX_TILE_H > 65535u) return 0;
+  return rows;
+}
+
+static dim3 fastGrid3(const TraceWork & w, uint64_t rows)
+{
+  const uint32_t tilesX = (w.fp.W + RFX_TILE_W - 1) / RFX_TILE_W, warps = SMALL_THREADS / 32;
+  return dim3((tilesX + warps - 1) / warps, (uint32_t)((rows + RFX_TILE_H - 1) / RFX_TILE_H));
+}
+
+uint32_t fastGridSize(const TraceWork & w)
+{
+  const uint64_t rows = fastRows(w);
+  if (!rows) return 0;
+  const dim3 g = fastGrid3(w, rows);
+  return g.x <= 65535u ? g.x * g.y : 0;
+}
+
+int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st, uint32_t * fastGrid)
+{
+  if (fastGrid) *fastGrid = 0;
   const FrameParams & fp = w.fp;
   uint64_t nThreads;
   int tiled = 0;
@@ -599,25 +698,18 @@ int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st
         rows = mine * fp.stripRows;
       }
       if (rows == 0) return 0;
-      const bool fast = fp.sampleNum == 1 && !fp.jitter && !w.image && !w.sigOut && w.argbOut && (uint64_t)fp.W * fp.H < (1ull << 32) &&
-                        (rows + RFX_TILE_H - 1) / RFX_TILE_H <= 65535u;
-      if (fast)
+      if (fastGridSize(w))
       {
-        const uint32_t tilesX = (fp.W + RFX_TILE_W - 1) / RFX_TILE_W, warps = SMALL_THREADS / 32;
-        const dim3 grid((tilesX + warps - 1) / warps, (uint32_t)((rows + RFX_TILE_H - 1) / RFX_TILE_H));
+        const dim3 grid = fastGrid3(w, fastRows(w));
+        if (fastGrid) *fastGrid = grid.x * grid.y;
         // scene features decide the instantiation: texel-free, plane-free, single-light scenes run the lean one
         bool texels = false;
         for (int i = 0; i < SMALL_MAX_TEX; i++) texels = texels || sc.tex[i].px != nullptr;
         const bool lean = !texels && sc.nP == 0 && sc.nL <= 1;
-#ifdef RFX_NO_LEAN
-        const bool useLean = false;
-#else
-        const bool useLean = lean;
-#endif
-        if (useLean)
-          k_trace_small<0><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W));
+        if (lean)
+          k_trace_small<0><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W), w.order);
         else
-          k_trace_small<F_ALL><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W));
+          k_trace_small<F_ALL><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W), w.order);
         return 1;
       }
       nThreads = (uint64_t)((fp.W + RFX_TILE_W - 1) / RFX_TILE_W) * ((rows + RFX_TILE_H - 1) / RFX_TILE_H) * 32;
