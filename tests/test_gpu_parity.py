@@ -237,3 +237,27 @@ def test_fast_kernel_equals_general_kernel_full_size(capi):
         assert a.stats()["rays"] == b.stats()["rays"]
     finally:
         a.close(); b.close()
+
+
+def test_tile_ordering_does_not_change_results(capi):
+    """Cost-ordered tile scheduling only permutes which CTA renders which tile group: frames rendered with the history of the
+    previous launch, without it, and across an image-size change (history dropped) are bit-identical."""
+    cams = S.orbit_cameras(9)[:4]
+    frames = {}
+    for on in (True, False):
+        c = capi.Context(0)
+        try:
+            c.load_scene(S.default_scene()); c.set_seeds(77, 77)
+            c.set_tile_ordering(on)
+            c.set_image_size(200, 120)
+            a = c.render_frames(cams, 20)            # frame 0 in index order, frames 1-3 in the order frame k-1 recorded
+            c.set_image_size(136, 96)                # different grid: the history must not be reused
+            b = c.render_frames(cams[:2], 20)
+            c.set_image_size(200, 120)
+            d = c.render_frames(cams[:1], 20)
+            frames[on] = (a, b, d, c.stats()["rays"])
+        finally:
+            c.close()
+    for x, y in zip(frames[True][:3], frames[False][:3]):
+        assert np.array_equal(x, y)
+    assert frames[True][3] == frames[False][3]
