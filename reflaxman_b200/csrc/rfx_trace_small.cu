@@ -495,7 +495,11 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
     rngTriple(s, rd.x, rd.y, rd.z);
     uint32_t sig = 0;
     const V3 c = traceSmall<false, FEAT>(sc, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, events, sig);
+#ifdef RFX_DEBUG_DEPTH
+    argbOut[q] = events;       // debug build (tools/depth_stats.py): bounce-loop iterations | shadow rays << 16 instead of the colour
+#else
     argbOut[q] = packArgb(c.x, c.y, c.z);
+#endif
   }
   if (ord.outLists)
   {
