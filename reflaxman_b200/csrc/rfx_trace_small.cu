@@ -41,7 +41,7 @@ namespace rfx
 #define RFX_SMALL_THREADS 128
 #endif
 #ifndef RFX_SMALL_MINBLOCKS
-#define RFX_SMALL_MINBLOCKS 7
+#define RFX_SMALL_MINBLOCKS 8      // fast kernel: 64 registers, no spills, 32 warps per SM
 #endif
 
 // Scene features a kernel instantiation supports.  The lean instantiation (FEAT = 0: no planes, no texels, one light) is
@@ -257,7 +257,10 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
   bool shadowQuery = false;
   int refl = 0, li = 0, hslot = -1;
   // what survives of the hit while its lights are being answered
-  V3 norm = ray, reflect = ray, color = mul, sumLight = pix, sumSpec = pix;
+  V3 norm = ray, reflect = ray, color = mul;
+  // light sums of the hit: loop-carried only when a hit can have a second shadow query (F_LIGHTS); with one light they are
+  // born in the shadow answer and die in the finish of the same trip, which frees six registers across the object loops
+  V3 carryLight = pix, carrySpec = pix;
   float normLen = 0.0f, reflectLen = 0.0f, mrefl = 0.0f;
   float rf = 0.0f;          // weight of the reflected continuation (Scene.cpp:196 / :207); its sign bit clear
   bool dielectric = false;
@@ -268,6 +271,8 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
     hit.dist = FLT_MAX; hit.slot = -1; hit.order = 0x7FFFFFFF; hit.t = 0; hit.u = 0; hit.v = 0;
     intersectSmall<FEAT>(sc, qo, qd, shadowQuery ? hslot : -1, shadowQuery, hit);
 
+    V3 sumLight = (FEAT & F_LIGHTS) ? carryLight : mk(0.0f, 0.0f, 0.0f);
+    V3 sumSpec = (FEAT & F_LIGHTS) ? carrySpec : mk(0.0f, 0.0f, 0.0f);
     if (!shadowQuery)
     {
       // ---- closest hit of the bounce segment (origin = qo, ray = qd), Scene.cpp:80-112
@@ -371,7 +376,7 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
 
     // ---- next light that faces the surface gets a shadow query, Scene.cpp:118-129
     bool cast = false;
-    const int nL = (FEAT & F_LIGHTS) ? sc.nL : (sc.nL > 0 ? 1 : 0);
+    const int nL = (FEAT & F_LIGHTS) ? sc.nL : ((sc.nL > 0 && !shadowQuery) ? 1 : 0);   // one light: an answered query is the last
     for (; li < nL; li++)
     {
       const Light & L = sc.light[li];
@@ -385,6 +390,7 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
     }
     if (cast)
     {
+      if (FEAT & F_LIGHTS) { carryLight = sumLight; carrySpec = sumSpec; }
       shadowQuery = true;
       events += 0x10000u;
       continue;
@@ -534,7 +540,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
 
 // General kernel: every mode of Render::renderNext (grid SSAA, block preview, additive jitter, arbitrary pixel slices,
 // float image, signatures).
-__global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_small_any(const __grid_constant__ SmallScene sc, const __grid_constant__ FrameParams fp,
+__global__ void __launch_bounds__(SMALL_THREADS, 6) k_trace_small_any(const __grid_constant__ SmallScene sc, const __grid_constant__ FrameParams fp,
                                                                const uint32_t * __restrict__ sampleStates, float * __restrict__ image,
                                                                uint32_t * __restrict__ argbOut, uint32_t * __restrict__ sigOut,
                                                                unsigned long long * __restrict__ counters, int tiled)

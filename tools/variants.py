@@ -10,10 +10,11 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "gpurun_variants")
 
 VARIANTS = {
-    # name: (defines, force_path, cost-ordered tile scheduling)
-    "index_order": ([], 1, 0),
-    "cost_order_8_classes": ([], 1, 1),
-    "cost_order_8_classes_b": (["RFX_TILE_BOUNDS={20u,14u,10u,7u,5u,3u,2u}"], 1, 1),
+    # name: (defines, force_path)
+    "t128_mb7": (["RFX_SMALL_MINBLOCKS=7"], 1),
+    "t128_mb8": (["RFX_SMALL_MINBLOCKS=8"], 1),
+    "t128_mb9": (["RFX_SMALL_MINBLOCKS=9"], 1),
+    "t64_mb16": (["RFX_SMALL_THREADS=64", "RFX_SMALL_MINBLOCKS=16"], 1),
 }
 
 
@@ -40,7 +41,6 @@ def run_one(name):
     c = capi.Context(0)
     c.load_scene(S.default_scene()); c.set_seeds(12345, 12345); c.set_image_size(1920, 1080)
     c.force_path(VARIANTS[name][1])
-    c.set_tile_ordering(VARIANTS[name][2])
     n = 8
     out = torch.empty((n, 1080, 1920), dtype=torch.int32, device="cuda")
     cams = capi.pack_cameras([S.default_camera()] * n)
