@@ -255,15 +255,15 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
   // (hslot >= 0 and shadowQuery): qo = drop, qd = the jittered ray towards light li, the hit object is ignored.
   V3 qo = origin, qd = ray;
   bool shadowQuery = false;
-  int refl = 0, li = 0, hslot = -1;
+  int li = 0, hslot = -1;   // (the segment index of the reference's loop is the low half of `events` minus one)
   // what survives of the hit while its lights are being answered
   V3 norm = ray, reflect = ray, color = mul;
   // light sums of the hit: loop-carried only when a hit can have a second shadow query (F_LIGHTS); with one light they are
   // born in the shadow answer and die in the finish of the same trip, which frees six registers across the object loops
   V3 carryLight = pix, carrySpec = pix;
   float normLen = 0.0f, reflectLen = 0.0f, mrefl = 0.0f;
-  float rf = 0.0f;          // weight of the reflected continuation (Scene.cpp:196 / :207); its sign bit clear
-  bool dielectric = false;
+  float rfs = 0.0f;         // weight of the reflected continuation (Scene.cpp:196 / :207), negated for metals (one register
+                            // for the weight and the material type; the weight is in [0.2, 1], never zero)
 
   for (;;)
   {
@@ -293,7 +293,7 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
       const Material & m = sc.mat[hit.slot];
       color = mk(m.r, m.g, m.b);
       mrefl = m.reflectivity;
-      dielectric = m.type == 1;
+      const bool dielectric = m.type == 1;
       hslot = hit.slot;
       if (hit.slot < SM_TRI_BIT)
       {
@@ -322,12 +322,12 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
       normLen = vlen(norm);
       reflectLen = vlen(reflect);
       // the continuation weight only depends on ray and norm: evaluate it while the ray is still in registers
-      rf = 0.8f;                                                           // metal, Scene.cpp:207
+      rfs = -0.8f;                                                         // metal, Scene.cpp:207
       if (dielectric)                                                      // Scene.cpp:192-196
       {
         const float a = vlen(qd) * normLen;
         const float cosA = (a > RFX_VSN) ? clamp01(((qd.x * -norm.x + qd.y * -norm.y) + qd.z * -norm.z) / a) : 0.0f;
-        rf = 0.2f + 0.8f * cubeLikePowf(1.0f - cosA);
+        rfs = 0.2f + 0.8f * cubeLikePowf(1.0f - cosA);
       }
       sumLight = mk(0.0f, 0.0f, 0.0f);
       sumSpec = mk(0.0f, 0.0f, 0.0f);
@@ -336,7 +336,7 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
     else
     {
       // ---- answer of the shadow query for light li, Scene.cpp:125-186
-      const Light & L = sc.light[li];
+      const Light & L = sc.light[(FEAT & F_LIGHTS) ? li : 0];
       const bool inShadow = hit.slot >= 0;
       if (SIG) RFX_SIG(sig, 0x100 + 2 * li + (inShadow ? 1 : 0));
       if (!inShadow)
@@ -399,6 +399,8 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
     // ---- all lights answered: finish the hit, Scene.cpp:189-226
     sumLight = mk(sc.ambient[0] * sc.ambientPower + sumLight.x, sc.ambient[1] * sc.ambientPower + sumLight.y,
                   sc.ambient[2] * sc.ambientPower + sumLight.z);         // Scene.cpp:189
+    const bool dielectric = rfs > 0.0f;
+    const float rf = fabsf(rfs);
     const float k = 1.0f - rf;
     const V3 fin = mk(((color.x * k) * sumLight.x + sumSpec.x) * mul.x, ((color.y * k) * sumLight.y + sumSpec.y) * mul.y,
                       ((color.z * k) * sumLight.z + sumSpec.z) * mul.z); // Scene.cpp:198-199 / 209-210
@@ -408,7 +410,7 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
     pix = mk(clamp01(pix.x + fin.x), clamp01(pix.y + fin.y), clamp01(pix.z + fin.z));
 
     if (mul.x < 0.01f && mul.y < 0.01f && mul.z < 0.01f) break;
-    if (++refl >= reflNumber) break;
+    if ((int)(events & 0xFFFFu) >= reflNumber) break;                    // ++refl < reflNumber, Scene.cpp:80
 
     // reflect.normalized(): its length is the reflectLen of the hit set-up (same operands, same operations), Vector3.cpp:55-64
     const V3 rn = (reflectLen > RFX_VSN) ? mk(reflect.x / reflectLen, reflect.y / reflectLen, reflect.z / reflectLen) : reflect;

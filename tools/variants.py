@@ -11,10 +11,9 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 
 VARIANTS = {
     # name: (defines, force_path)
-    "t128_mb7": (["RFX_SMALL_MINBLOCKS=7"], 1),
     "t128_mb8": (["RFX_SMALL_MINBLOCKS=8"], 1),
     "t128_mb9": (["RFX_SMALL_MINBLOCKS=9"], 1),
-    "t64_mb16": (["RFX_SMALL_THREADS=64", "RFX_SMALL_MINBLOCKS=16"], 1),
+    "t64_mb18": (["RFX_SMALL_THREADS=64", "RFX_SMALL_MINBLOCKS=18"], 1),
 }
 
 
