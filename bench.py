@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 W, H, DEPTH = 1920, 1080, 20
 CENSUS_FLOP_PER_PIXEL = 1301.7          # SURVEY.md §8(d), config 2 (our own census build counts 1270.9)
-NCU_DRAM_BYTES_PER_LAUNCH = 8329216     # dram__bytes_read.sum + dram__bytes_write.sum of k_trace_small, profiles/r1_final (ncu --set full)
+NCU_DRAM_BYTES_PER_LAUNCH = 8396800     # dram__bytes_read.sum + dram__bytes_write.sum of k_trace_small, profiles/r1_final (ncu --set full)
 RAYS_PER_FRAME_CANONICAL = 7493076      # oracle counters, config 2, seed 12345 (3.6136 rays/pixel); recomputed live when possible
 METRIC = "Mrays/s at 1920x1080, default scene, reflection depth 20 (frames/s alongside)"
 
