@@ -152,8 +152,8 @@ struct rfx_ctx
   uint32_t * dRng = nullptr;  // [2] ping-pong LCG state of the Vector3.cpp TU stream
   int rngSlot = 0;
   uint32_t seedRender = 12345u;
-  uint32_t * dBlockCounts = nullptr, * dBlockOffsets = nullptr; size_t blocksCap = 0, offsCap = 0;
-  uint8_t * dAcceptMasks = nullptr; size_t masksCap = 0;
+  uint32_t * dRngPrefix = nullptr;            // [3][RNG_CLASS_BLOCKS + 1] accept-count prefix sums of the LCG cycle (built at creation)
+  RngLocate * dRngLocate = nullptr;
   uint32_t * dSampleStates = nullptr; size_t statesCap = 0;
   int * dStatus = nullptr;
   float * dRays = nullptr; size_t raysCap = 0;   // rfx_trace_rays scratch
@@ -398,16 +398,12 @@ int rankSamples(rfx_ctx * ctx, uint64_t n, bool skipOnly, cudaStream_t st, uint6
   if (n == 0) return RFX_OK;
   const uint32_t nBlocks = rngBlocksFor(n);
   int rc;
-  if ((rc = ensure(ctx, ctx->dBlockCounts, ctx->blocksCap, nBlocks)) != RFX_OK) return rc;
-  if ((rc = ensure(ctx, ctx->dBlockOffsets, ctx->offsCap, nBlocks)) != RFX_OK) return rc;
-  if ((rc = ensure(ctx, ctx->dAcceptMasks, ctx->masksCap, (size_t)nBlocks * RNG_THREADS)) != RFX_OK) return rc;
   if (!skipOnly && (rc = ensure(ctx, ctx->dSampleStates, ctx->statesCap, n)) != RFX_OK) return rc;
   RngWork w;
   w.stateIn = ctx->dRng + ctx->rngSlot;
   w.stateOut = ctx->dRng + (ctx->rngSlot ^ 1);
-  w.blockCounts = ctx->dBlockCounts;
-  w.blockOffsets = ctx->dBlockOffsets;
-  w.acceptMasks = ctx->dAcceptMasks;
+  w.prefix = ctx->dRngPrefix;
+  w.locate = ctx->dRngLocate;
   w.sampleStates = skipOnly ? nullptr : ctx->dSampleStates;
   w.status = ctx->dStatus;
   w.n = n;
@@ -553,6 +549,16 @@ int rfx_create(rfx_ctx ** out, int device)
   step(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
   if (initRngTables() != 0) step(cudaErrorUnknown);
   step(cudaMalloc((void **)&ctx->dRng, 2 * sizeof(uint32_t)));
+  step(cudaMalloc((void **)&ctx->dRngPrefix, 3 * (size_t)(RNG_CLASS_BLOCKS + 1) * sizeof(uint32_t)));
+  step(cudaMalloc((void **)&ctx->dRngLocate, sizeof(RngLocate)));
+  if (err == cudaSuccess)
+  {
+    // accept counts of the whole LCG cycle: ~5 ms once per context; every later ranking or skip is a table lookup away
+    uint32_t * counts = nullptr;
+    step(cudaMalloc((void **)&counts, 3 * (size_t)RNG_CLASS_BLOCKS * sizeof(uint32_t)));
+    if (err == cudaSuccess) { launchRngTable(counts, ctx->dRngPrefix, ctx->stream); step(cudaStreamSynchronize(ctx->stream)); step(cudaGetLastError()); }
+    cudaFree(counts);
+  }
   step(cudaMalloc((void **)&ctx->dStatus, sizeof(int)));
   step(cudaMalloc((void **)&ctx->dCounters, 64 * sizeof(unsigned long long)));
   step(cudaMalloc((void **)&ctx->dLut, 256 * sizeof(float)));
@@ -588,8 +594,8 @@ void rfx_destroy(rfx_ctx * ctx)
   cudaDeviceSynchronize();
   for (HostTex & t : ctx->tex) if (t.dev) cudaFree(t.dev);
   cudaFree(ctx->dBlob); cudaFree(ctx->dLut); cudaFree(ctx->dImage); cudaFree(ctx->dSig); cudaFree(ctx->dRng);
-  cudaFree(ctx->dBlockCounts); cudaFree(ctx->dBlockOffsets); cudaFree(ctx->dSampleStates); cudaFree(ctx->dStatus);
-  cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dAcceptMasks); cudaFree(ctx->dBvhNodes); cudaFree(ctx->dBvhPrims); cudaFree(ctx->dTileLists[0]); cudaFree(ctx->dTileLists[1]); cudaFree(ctx->dTileCounts);
+  cudaFree(ctx->dRngPrefix); cudaFree(ctx->dRngLocate); cudaFree(ctx->dSampleStates); cudaFree(ctx->dStatus);
+  cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dBvhNodes); cudaFree(ctx->dBvhPrims); cudaFree(ctx->dTileLists[0]); cudaFree(ctx->dTileLists[1]); cudaFree(ctx->dTileCounts);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   for (int i = 0; i < 3; i++)
   {

@@ -32,85 +32,135 @@ namespace rfx
 
 uint32_t lcgJumpHost(uint32_t s, uint64_t n) { return lcgJump(s, (uint32_t)n); }
 
-// Jump-ahead tables for K1.  n draws ahead is the affine map s -> A_n s + C_n; thread t of block b starts
-// (b * RNG_TRIPLES_PER_BLOCK + t * RNG_TRIPLES_PER_THREAD) triples into the pass.  The block part is applied nibble by nibble
-// of b (6 table steps cover 2^24 blocks; the largest pass, a 2^28-sample stream skip, has 2^18), the thread part is one step: ~30 instructions instead of a 28-round binary powering.
-__constant__ uint32_t c_jumpBlock[6][16][2];   // [nibble position][nibble value] -> (A, C) of (value << 4*pos) * 3 * RNG_TRIPLES_PER_BLOCK draws
+// =====================================================================================================================
+// K1 — ranking the rejection-sampled LCG stream (reference Vector3.cpp:176-188, trace_math.h:34-39)
+//
+// Scene::trace call #q of a process owns the q-th ACCEPTED draw-triple of one LCG.  Whether a triple is accepted depends only
+// on the LCG state it starts from, and that LCG (a = 214013 = 1 mod 4, c odd) walks ONE cycle through all 2^32 states.  So
+// the accept pattern is a fixed sequence over the cycle, independent of the seed; the seed only says where on the cycle the
+// stream starts.  Write pos(s) for the number of steps from state 0 to state s.  A stream that starts at position p0 visits
+// the triples that start at positions p0, p0 + 3, p0 + 6, ... (mod 2^32): all in residue class p0 mod 3 until the position
+// wraps, then in the class the wrapped position falls into (2^32 = 1 mod 3: classes follow each other 0 -> 2 -> 1 -> 0).
+//
+//   k_rng_table   (once per context, ~5 ms, 8.4 MB)  for every class r and every block of 2048 consecutive triples of the
+//                 class: how many are accepted; k_rng_prefix turns the counts into exclusive prefix sums per class
+//   k_rng_locate  (one CTA per pass)  pos(seed state) by a 32-step bitwise discrete logarithm (the low k bits of an LCG
+//                 mod 2^32 have period 2^k), then the stream's offset inside its class from the table and one partially
+//                 evaluated block.  For a skip-only pass (rfx_skip_samples, frame sharding) it also finds the triple that
+//                 holds the last rank by binary search in the table: skipping any number of samples costs one small CTA
+//   k_rng_rank    one CTA per block of the class that can hold wanted ranks: its first rank comes from the table, its
+//                 2048 accept tests run once, the accepted states are scattered to their ranks.  Blocks do not depend on
+//                 each other (no count pass, no scan between blocks), and a GPU that owns part of a frame only evaluates
+//                 the blocks that hold its ranks
+// =====================================================================================================================
+__constant__ uint32_t c_jumpBlock[5][16][2];   // [nibble position][nibble value] -> (A, C) of (value << 4*pos) * 3 * RNG_TRIPLES_PER_BLOCK draws
+__constant__ uint32_t c_jumpPow2[32][2];       // k -> (A, C) of 2^k draws (discrete logarithm)
+__constant__ uint32_t c_classStart[3];         // state at position r = 0, 1, 2
 __device__ uint2 g_jumpThread[RNG_THREADS];    // t -> (A, C) of t * 3 * RNG_TRIPLES_PER_THREAD draws (global: one coalesced 8-byte load per thread;
                                                // a per-lane index into the constant bank would serialise 32 ways)
 
 int initRngTables()
 {
-  static uint32_t blk[6][16][2], thr[RNG_THREADS][2];
+  static uint32_t blk[5][16][2], thr[RNG_THREADS][2], p2[32][2], cls[3];
   auto affine = [](uint64_t draws, uint32_t out[2]) {
     const uint32_t c = lcgJump(0u, (uint32_t)draws);          // f^n(0) = C_n
     out[0] = lcgJump(1u, (uint32_t)draws) - c;                // f^n(1) - C_n = A_n
     out[1] = c;
   };
-  for (int pos = 0; pos < 6; pos++)
+  for (int pos = 0; pos < 5; pos++)
     for (uint64_t v = 0; v < 16; v++) affine((v << (4 * pos)) * 3ull * RNG_TRIPLES_PER_BLOCK, blk[pos][v]);
   for (uint64_t t = 0; t < RNG_THREADS; t++) affine(t * 3ull * RNG_TRIPLES_PER_THREAD, thr[t]);
+  for (int k = 0; k < 32; k++) affine(1ull << k, p2[k]);
+  for (uint32_t r = 0; r < 3; r++) cls[r] = lcgJump(0u, r);
   if (cudaMemcpyToSymbol(c_jumpBlock, blk, sizeof(blk)) != cudaSuccess) return 1;
   if (cudaMemcpyToSymbol(g_jumpThread, thr, sizeof(thr)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(c_jumpPow2, p2, sizeof(p2)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(c_classStart, cls, sizeof(cls)) != cudaSuccess) return 1;
   return 0;
 }
 
-// LCG state at the first triple of this thread
-__device__ __forceinline__ uint32_t rngThreadStart(uint32_t s)
+// triples of class r: positions r, r + 3, ... below 2^32
+__device__ __forceinline__ uint32_t rngClassTriples(uint32_t r) { return r == 0 ? 1431655766u : 1431655765u; }
+
+// LCG state at the first triple of this thread in block j of class r (block j starts at position r + 6144 j)
+__device__ __forceinline__ uint32_t rngThreadStart(uint32_t r, uint32_t j)
 {
-  uint32_t b = blockIdx.x;
+  uint32_t s = c_classStart[r];
 #pragma unroll
-  for (int pos = 0; pos < 6; pos++, b >>= 4)
+  for (int pos = 0; pos < 5; pos++, j >>= 4)
   {
-    if (b == 0) break;                                         // uniform
-    const uint32_t v = b & 15u;
+    if (j == 0) break;                                         // uniform
+    const uint32_t v = j & 15u;
     s = c_jumpBlock[pos][v][0] * s + c_jumpBlock[pos][v][1];
   }
   const uint2 m = __ldg(&g_jumpThread[threadIdx.x]);
   return m.x * s + m.y;
 }
 
-__global__ void __launch_bounds__(RNG_THREADS) k_rng_count(const uint32_t * __restrict__ stateIn, uint32_t * __restrict__ blockCounts,
-                                                           uint8_t * __restrict__ acceptMasks)
+// accept bits of this thread's RNG_TRIPLES_PER_THREAD triples (bit k = triple k); triples past the end of the class are cleared
+__device__ __forceinline__ uint32_t rngThreadMask(uint32_t sStart, uint32_t r, uint32_t j)
 {
-  __shared__ int warpSums[RNG_THREADS / 32];
-  const uint32_t gid = blockIdx.x * RNG_THREADS + threadIdx.x;
-  uint32_t s = rngThreadStart(*stateIn);
-  uint32_t mask = 0;
+  uint32_t s = sStart, mask = 0;
 #pragma unroll
   for (int k = 0; k < RNG_TRIPLES_PER_THREAD; k++)
   {
     float x, y, z;
     if (rngTriple(s, x, y, z)) mask |= 1u << k;
   }
-  acceptMasks[gid] = (uint8_t)mask;   // the scatter pass re-walks the integer LCG only; the float accept test runs once
-  int cnt = __popc(mask);
-  cnt = __reduce_add_sync(0xffffffffu, cnt);
-  if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0)
-  {
-    int t = 0;
-#pragma unroll
-    for (int w = 0; w < RNG_THREADS / 32; w++) t += warpSums[w];
-    blockCounts[blockIdx.x] = (uint32_t)t;
-  }
+  const uint32_t qFirst = j * RNG_TRIPLES_PER_BLOCK + threadIdx.x * RNG_TRIPLES_PER_THREAD, nr = rngClassTriples(r);
+  if (qFirst + RNG_TRIPLES_PER_THREAD > nr) mask &= qFirst >= nr ? 0u : ((1u << (nr - qFirst)) - 1u);
+  return mask;
 }
 
-// single-CTA exclusive scan of the per-block accept counts (a few thousand to a few hundred thousand entries):
-// coalesced 1024-wide tiles, warp-shuffle scan inside each tile, running carry between tiles
-__global__ void __launch_bounds__(1024) k_rng_scan(const uint32_t * __restrict__ counts, uint32_t * __restrict__ offsets,
-                                                   uint32_t nBlocks, unsigned long long n, int * status)
+// exclusive prefix of v over the CTA (RNG_THREADS threads); total receives the CTA sum
+__device__ __forceinline__ int rngBlockScan(int v, int & total)
+{
+  __shared__ int warpSums[RNG_THREADS / 32];
+  int incl = v;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1)
+  {
+    const int t = __shfl_up_sync(0xffffffffu, incl, off);
+    if ((threadIdx.x & 31) >= off) incl += t;
+  }
+  __syncthreads();                                             // warpSums may still be read from a previous call
+  if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  int wbase = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < RNG_THREADS / 32; w++)
+  {
+    if (w < (int)(threadIdx.x >> 5)) wbase += warpSums[w];
+    all += warpSums[w];
+  }
+  total = all;
+  return wbase + incl - v;
+}
+
+__global__ void __launch_bounds__(RNG_THREADS) k_rng_table(uint32_t * __restrict__ counts)
+{
+  const uint32_t r = blockIdx.y, j = blockIdx.x;
+  const uint32_t mask = rngThreadMask(rngThreadStart(r, j), r, j);
+  int total;
+  rngBlockScan(__popc(mask), total);
+  if (threadIdx.x == 0) counts[r * RNG_CLASS_BLOCKS + j] = (uint32_t)total;
+}
+
+// one CTA per class: prefix[r][j] = accepted triples of class r in blocks < j, j = 0 .. RNG_CLASS_BLOCKS (the last entry is the class total)
+__global__ void __launch_bounds__(1024) k_rng_prefix(const uint32_t * __restrict__ counts, uint32_t * __restrict__ prefix)
 {
   __shared__ uint32_t warpTot[32];
-  __shared__ unsigned long long carryS;
+  __shared__ uint32_t carryS;
+  const uint32_t r = blockIdx.x;
+  counts += r * RNG_CLASS_BLOCKS;
+  prefix += r * (RNG_CLASS_BLOCKS + 1);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carryS = 0ull;
+  if (threadIdx.x == 0) carryS = 0u;
   __syncthreads();
-  for (uint32_t base = 0; base < nBlocks; base += 1024u)
+  for (uint32_t base = 0; base < RNG_CLASS_BLOCKS; base += 1024u)
   {
     const uint32_t idx = base + threadIdx.x;
-    const uint32_t v = idx < nBlocks ? counts[idx] : 0u;
+    const uint32_t v = idx < RNG_CLASS_BLOCKS ? counts[idx] : 0u;
     uint32_t incl = v;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1)
@@ -120,8 +170,7 @@ __global__ void __launch_bounds__(1024) k_rng_scan(const uint32_t * __restrict__
     }
     if (lane == 31u) warpTot[warp] = incl;
     __syncthreads();
-    const unsigned long long carry = carryS;
-    // every warp scans the 32 warp totals redundantly (cheaper than another barrier)
+    const uint32_t carry = carryS;
     uint32_t wt = warpTot[lane], winc = wt;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1)
@@ -131,58 +180,121 @@ __global__ void __launch_bounds__(1024) k_rng_scan(const uint32_t * __restrict__
     }
     const uint32_t warpBase = __shfl_sync(0xffffffffu, winc - wt, warp);
     const uint32_t tileTotal = __shfl_sync(0xffffffffu, winc, 31);
-    if (idx < nBlocks)
-    {
-      // offsets saturate at 2^32-1: any block whose offset is >= n is skipped by the scatter pass anyway
-      const unsigned long long o = carry + warpBase + (incl - v);
-      offsets[idx] = o > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)o;
-    }
+    if (idx < RNG_CLASS_BLOCKS) prefix[idx] = carry + warpBase + (incl - v);
     __syncthreads();
     if (threadIdx.x == 0) carryS = carry + tileTotal;
     __syncthreads();
   }
-  if (threadIdx.x == 0 && carryS < n) *status = 1;
+  if (threadIdx.x == 0) prefix[RNG_CLASS_BLOCKS] = carryS;
 }
 
-__global__ void __launch_bounds__(RNG_THREADS) k_rng_scatter(const uint32_t * __restrict__ stateIn, uint32_t * __restrict__ stateOut,
-                                                             const uint32_t * __restrict__ blockOffsets, const uint8_t * __restrict__ acceptMasks,
-                                                             uint32_t * __restrict__ sampleStates, unsigned long long n, uint32_t rankBase,
-                                                             unsigned long long ownPeriod, uint32_t ownWorld, uint32_t ownRank)
+__global__ void __launch_bounds__(RNG_THREADS) k_rng_locate(const uint32_t * __restrict__ stateIn, const uint32_t * __restrict__ prefix,
+                                                            unsigned long long n, RngLocate * __restrict__ loc,
+                                                            uint32_t * __restrict__ stateOut /* skip-only pass: where the stream ends; else NULL */,
+                                                            int * __restrict__ status)
 {
-  __shared__ int warpSums[RNG_THREADS / 32];
-  const unsigned long long boff = (unsigned long long)blockOffsets[blockIdx.x] + rankBase;
-  if (boff >= n) return;   // uniform per CTA
-  // skip-only pass (rfx_skip_samples): nothing to store, only the CTA that can hold rank n-1 has work (the stream-end state)
-  if (!sampleStates && boff + RNG_TRIPLES_PER_BLOCK - 1 < n - 1) return;
+  __shared__ uint32_t shPos, shBlock, shClass;
+  __shared__ unsigned long long shWant;
+  if (threadIdx.x == 0)
+  {
+    // pos(s): bit k of the position is set exactly when the state reached with the lower bits differs from s in bit k
+    const uint32_t s = *stateIn;
+    uint32_t pos = 0, t = 0;
+    for (int k = 0; k < 32; k++)
+      if (((t ^ s) >> k) & 1u) { t = c_jumpPow2[k][0] * t + c_jumpPow2[k][1]; pos |= 1u << k; }
+    shPos = pos;
+  }
+  __syncthreads();
+  const uint32_t p0 = shPos, r0 = p0 % 3u, q0 = p0 / 3u, j0 = q0 / RNG_TRIPLES_PER_BLOCK;
+  const uint32_t r1 = r0 == 0 ? 2u : r0 - 1u;                  // class after the wrap
+  const uint32_t * pre0 = prefix + r0 * (RNG_CLASS_BLOCKS + 1), * pre1 = prefix + r1 * (RNG_CLASS_BLOCKS + 1);
+
+  // accepted triples of the class before the stream's first triple: whole blocks from the table, block j0 by evaluation
+  const uint32_t qFirst = j0 * RNG_TRIPLES_PER_BLOCK + threadIdx.x * RNG_TRIPLES_PER_THREAD;
+  uint32_t mask = rngThreadMask(rngThreadStart(r0, j0), r0, j0);
+  const uint32_t before = q0 <= qFirst ? 0u : min(q0 - qFirst, (uint32_t)RNG_TRIPLES_PER_THREAD);
+  int partial;
+  rngBlockScan(__popc(mask & ((1u << before) - 1u)), partial);
+  const unsigned long long off1 = (unsigned long long)pre0[j0] + (unsigned long long)partial;   // accepted before the stream in class r0
+  const unsigned long long seg1 = (unsigned long long)pre0[RNG_CLASS_BLOCKS] - off1;            // accepted from the stream start to the wrap
+  if (threadIdx.x == 0)
+  {
+    loc->r0 = r0; loc->j0 = j0; loc->r1 = r1; loc->nb1 = RNG_CLASS_BLOCKS - j0; loc->off1 = off1; loc->seg1 = seg1;
+  }
+  if (!stateOut) return;
+
+  // ---- skip-only pass: the triple holding rank n-1 is the want-th accepted triple of its class
+  if (threadIdx.x == 0)
+  {
+    uint32_t cls = r0;
+    unsigned long long want = off1 + n;
+    const uint32_t * pre = pre0;
+    if (n > seg1) { cls = r1; want = n - seg1; pre = pre1; }
+    if (want > pre[RNG_CLASS_BLOCKS]) { *status = 1; want = pre[RNG_CLASS_BLOCKS]; }   // more than two classes in one pass: callers chunk below that
+    uint32_t lo = 0, hi = RNG_CLASS_BLOCKS - 1;                 // smallest block with pre[block + 1] >= want
+    while (lo < hi)
+    {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (pre[mid + 1] >= want) hi = mid; else lo = mid + 1;
+    }
+    shBlock = lo; shClass = cls; shWant = want;
+  }
+  __syncthreads();
+  const uint32_t cls = shClass, jE = shBlock;
+  const uint32_t sStart = rngThreadStart(cls, jE);
+  mask = rngThreadMask(sStart, cls, jE);
+  int total;
+  unsigned long long cum = (unsigned long long)(prefix + cls * (RNG_CLASS_BLOCKS + 1))[jE] + (unsigned long long)rngBlockScan(__popc(mask), total);
+  uint32_t s = sStart;
+#pragma unroll
+  for (int k = 0; k < RNG_TRIPLES_PER_THREAD; k++)
+  {
+    s = 214013u * s + 2531011u;
+    s = 214013u * s + 2531011u;
+    s = 214013u * s + 2531011u;
+    if (mask & (1u << k))
+    {
+      cum++;
+      if (cum == shWant) *stateOut = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RNG_THREADS) k_rng_rank(const RngLocate * __restrict__ loc, const uint32_t * __restrict__ prefix,
+                                                          uint32_t * __restrict__ stateOut, uint32_t * __restrict__ sampleStates,
+                                                          unsigned long long n, unsigned long long ownPeriod, uint32_t ownWorld, uint32_t ownRank,
+                                                          int * __restrict__ status)
+{
+  // virtual block v of the pass -> block j of class r; ranks of the stream = table prefix + local prefix - off
+  const uint32_t v = blockIdx.x, nb1 = loc->nb1;
+  uint32_t r, j;
+  long long off;
+  if (v < nb1) { r = loc->r0; j = loc->j0 + v; off = (long long)loc->off1; }
+  else         { r = loc->r1; j = v - nb1;     off = -(long long)loc->seg1; }
+  const bool lastBlock = v == gridDim.x - 1;
+  if (j >= RNG_CLASS_BLOCKS)
+  {
+    if (lastBlock && threadIdx.x == 0) *status = 1;             // a third class in one pass: callers chunk below that
+    return;
+  }
+  const uint32_t * pre = prefix + r * (RNG_CLASS_BLOCKS + 1);
+  const long long first = (long long)pre[j] - off, next = (long long)pre[j + 1] - off;   // ranks [first, next) start in this block
+  if (lastBlock && next < (long long)n && threadIdx.x == 0) *status = 1;                  // the provisioned blocks do not reach rank n-1
+  if (first >= (long long)n || next <= 0) return;                                         // uniform per CTA
   if (ownWorld)
   {
-    // split frames: a CTA whose whole rank range lies in one strip of another GPU has nothing to store (the stream-end
-    // state is written by whoever holds rank n-1, so the CTA that may contain it is never skipped)
-    const unsigned long long last = boff + RNG_TRIPLES_PER_BLOCK - 1;   // upper bound of the ranks this CTA can hold
-    const unsigned long long s0 = boff / ownPeriod, s1 = last / ownPeriod;
-    if (s0 == s1 && (uint32_t)(s0 % ownWorld) != ownRank && last < n - 1) return;
+    // split frames: a CTA whose ranks all lie in one strip of another GPU has nothing to store (the stream-end state is
+    // written by whoever holds rank n-1, so that CTA is never skipped)
+    const unsigned long long lo = (unsigned long long)(first < 0 ? 0 : first), hi = (unsigned long long)(next > (long long)n ? (long long)n : next) - 1ull;
+    const unsigned long long s0 = lo / ownPeriod, s1 = hi / ownPeriod;
+    if (s0 == s1 && (uint32_t)(s0 % ownWorld) != ownRank && hi < n - 1) return;
   }
 
-  const uint32_t gid = blockIdx.x * RNG_THREADS + threadIdx.x;
-  const uint32_t sStart = rngThreadStart(*stateIn);
+  const uint32_t sStart = rngThreadStart(r, j);
+  const uint32_t mask = rngThreadMask(sStart, r, j);
+  int total;
+  long long rank = first + (long long)rngBlockScan(__popc(mask), total);
   uint32_t s = sStart;
-  const uint32_t mask = acceptMasks[gid];
-  const int cnt = __popc(mask);
-  // block-wide exclusive scan of cnt
-  int incl = cnt;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1)
-  {
-    const int v = __shfl_up_sync(0xffffffffu, incl, off);
-    if ((threadIdx.x & 31) >= off) incl += v;
-  }
-  if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = incl;
-  __syncthreads();
-  int wbase = 0;
-  for (int w = 0; w < (int)(threadIdx.x >> 5); w++) wbase += warpSums[w];
-  unsigned long long rank = boff + (unsigned long long)(wbase + incl - cnt);
-
-  s = sStart;
 #pragma unroll
   for (int k = 0; k < RNG_TRIPLES_PER_THREAD; k++)
   {
@@ -192,10 +304,10 @@ __global__ void __launch_bounds__(RNG_THREADS) k_rng_scatter(const uint32_t * __
     s = 214013u * s + 2531011u;
     if (mask & (1u << k))
     {
-      if (rank < n)
+      if (rank >= 0 && rank < (long long)n)                     // negative: triples of block j0 before the stream's first
       {
-        if (sampleStates && (!ownWorld || (uint32_t)((rank / ownPeriod) % ownWorld) == ownRank)) sampleStates[rank] = before;
-        if (rank == n - 1) *stateOut = s;
+        if (!ownWorld || (uint32_t)(((unsigned long long)rank / ownPeriod) % ownWorld) == ownRank) sampleStates[rank] = before;
+        if (rank == (long long)n - 1) *stateOut = s;
       }
       rank++;
     }
@@ -204,18 +316,30 @@ __global__ void __launch_bounds__(RNG_THREADS) k_rng_scatter(const uint32_t * __
 
 uint32_t rngBlocksFor(uint64_t n)
 {
-  // acceptance is pi/6 = 0.5236 (1.91 triples per sample); 2n + 4096 triples leaves > 7 sigma of slack for every n
+  // acceptance is pi/6 = 0.5236 (1.91 triples per sample); 2n + 4096 triples leaves > 7 sigma of slack for every n; two more
+  // blocks for the partial blocks at the stream start and at the end of a class
   const uint64_t triples = 2 * n + 4096;
-  return (uint32_t)((triples + RNG_TRIPLES_PER_BLOCK - 1) / RNG_TRIPLES_PER_BLOCK);
+  return (uint32_t)((triples + RNG_TRIPLES_PER_BLOCK - 1) / RNG_TRIPLES_PER_BLOCK) + 2u;
+}
+
+int launchRngTable(uint32_t * counts, uint32_t * prefix, cudaStream_t st)
+{
+  k_rng_table<<<dim3(RNG_CLASS_BLOCKS, 3), RNG_THREADS, 0, st>>>(counts);
+  k_rng_prefix<<<3, 1024, 0, st>>>(counts, prefix);
+  return 2;
 }
 
 int launchRngRank(const RngWork & w, cudaStream_t st)
 {
-  k_rng_count<<<w.nBlocks, RNG_THREADS, 0, st>>>(w.stateIn, w.blockCounts, w.acceptMasks);
-  k_rng_scan<<<1, 1024, 0, st>>>(w.blockCounts, w.blockOffsets, w.nBlocks, (unsigned long long)w.n, w.status);
-  k_rng_scatter<<<w.nBlocks, RNG_THREADS, 0, st>>>(w.stateIn, w.stateOut, w.blockOffsets, w.acceptMasks, w.sampleStates, (unsigned long long)w.n, 0u,
-                                                      (unsigned long long)w.ownPeriod, w.ownWorld, w.ownRank);
-  return 3;
+  if (!w.sampleStates)
+  {
+    k_rng_locate<<<1, RNG_THREADS, 0, st>>>(w.stateIn, w.prefix, (unsigned long long)w.n, w.locate, w.stateOut, w.status);
+    return 1;
+  }
+  k_rng_locate<<<1, RNG_THREADS, 0, st>>>(w.stateIn, w.prefix, (unsigned long long)w.n, w.locate, nullptr, w.status);
+  k_rng_rank<<<w.nBlocks, RNG_THREADS, 0, st>>>(w.locate, w.prefix, w.stateOut, w.sampleStates, (unsigned long long)w.n,
+                                                 (unsigned long long)w.ownPeriod, w.ownWorld, w.ownRank, w.status);
+  return 2;
 }
 
 // =====================================================================================================================

@@ -10,21 +10,29 @@ namespace rfx
 // ---- K1: randDir stream ranking -------------------------------------------------------------------------------
 // The reference draws one Vector3::randomInsideSphere per Scene::trace call from a single serial LCG with rejection
 // sampling (reference Vector3.cpp:176-188, trace_math.h:34-39).  Trace call #p therefore owns the p-th ACCEPTED
-// draw-triple of the stream.  K1 reproduces that in parallel: LCG jump-ahead to every triple, accept flag, exclusive
-// scan, scatter of the LCG state that precedes each accepted triple.
+// draw-triple of the stream.  K1 reproduces that in parallel from a table of the accept counts of the LCG's whole
+// 2^32-state cycle (see the K1 header comment in rfx_kernels.cu).
 constexpr int RNG_THREADS = 256;
 constexpr int RNG_TRIPLES_PER_THREAD = 8;
 constexpr int RNG_TRIPLES_PER_BLOCK = RNG_THREADS * RNG_TRIPLES_PER_THREAD;
+constexpr uint32_t RNG_CLASS_BLOCKS = 699051;   // ceil(1431655766 / 2048): blocks of 2048 triples per residue class of start positions
+
+struct RngLocate                // written by k_rng_locate, read by k_rng_rank: where on the cycle this pass starts
+{
+  uint32_t r0, j0;              // residue class of the start position and the block of that class holding it
+  uint32_t r1, nb1;             // class after the wrap; virtual blocks [0, nb1) are blocks j0.. of class r0, the rest blocks 0.. of r1
+  unsigned long long off1;      // accepted triples of class r0 before the stream's first triple
+  unsigned long long seg1;      // accepted triples from the stream's first triple to the wrap
+};
 
 struct RngWork
 {
   const uint32_t * stateIn;     // device: LCG state before the first triple
   uint32_t * stateOut;          // device: LCG state after the triple that holds rank n-1
-  uint32_t * blockCounts;       // device scratch [nBlocks]
-  uint32_t * blockOffsets;      // device scratch [nBlocks]
-  uint8_t * acceptMasks;        // device scratch [nBlocks * RNG_THREADS]: 8 accept bits per thread, count -> scatter
-  uint32_t * sampleStates;      // device out [n] (may be NULL: skip-only)
-  int * status;                 // device: set to 1 when fewer than n triples were accepted in nBlocks blocks
+  const uint32_t * prefix;      // device [3][RNG_CLASS_BLOCKS + 1]: exclusive prefix sums of the per-block accept counts of the cycle
+  RngLocate * locate;           // device scratch
+  uint32_t * sampleStates;      // device out [n] (NULL: skip-only — one small CTA whatever n is)
+  int * status;                 // device: set to 1 when the provisioned blocks do not hold n accepted triples
   uint64_t n;                   // accepted triples wanted
   uint32_t nBlocks;
   // optional scatter filter (split frames): only ranks r with (r / ownPeriod) % ownWorld == ownRank are stored (ownWorld = 0: all)
@@ -33,9 +41,11 @@ struct RngWork
 };
 // uploads K1's jump-ahead tables to the current device (once per context); 0 = ok
 int initRngTables();
+// fills the cycle's accept-count table: counts [3][RNG_CLASS_BLOCKS] scratch, prefix [3][RNG_CLASS_BLOCKS + 1]; returns kernels launched
+int launchRngTable(uint32_t * counts, uint32_t * prefix, cudaStream_t st);
 // number of blocks that over-provisions n accepted triples (acceptance pi/6 = 0.5236)
 uint32_t rngBlocksFor(uint64_t n);
-// enqueue count + scan + scatter; returns the number of kernels launched
+// enqueue locate (+ rank); returns the number of kernels launched
 int launchRngRank(const RngWork & w, cudaStream_t st);
 
 // ---- K2: trace + shade ----------------------------------------------------------------------------------------

@@ -261,3 +261,42 @@ def test_tile_ordering_does_not_change_results(capi):
     for x, y in zip(frames[True][:3], frames[False][:3]):
         assert np.array_equal(x, y)
     assert frames[True][3] == frames[False][3]
+
+
+def _lcg_state_at(position):
+    """state of the reference's LCG (trace_math.h:36-39) `position` steps after state 0"""
+    a, c, s, n = 214013, 2531011, 0, position
+    while n:
+        if n & 1:
+            s = (a * s + c) & 0xFFFFFFFF
+        c = (c * (a + 1)) & 0xFFFFFFFF
+        a = (a * a) & 0xFFFFFFFF
+        n >>= 1
+    return s
+
+
+@pytest.mark.parametrize("back", [3001, 3002, 3003])
+def test_random_stream_across_the_lcg_cycle_wrap(capi, oracle, back):
+    """K1 ranks the stream from a table over the LCG's 2^32-state cycle; a stream that starts just before the end of the cycle
+    changes residue class when the position wraps.  Two frames from such a seed (all three classes), and a context that skips
+    the first frame, against the oracle's serial LCG."""
+    W, H, refl = 64, 48, 6
+    seed = _lcg_state_at((1 << 32) - back)
+    cams = S.orbit_cameras(5)[:2]
+    o = oracle.OracleRender(S.default_scene(), W, H, seed=seed)
+    want = [o.render(cam, refl).resolve()[1] for cam in cams]
+    c = capi.Context(0)
+    d = capi.Context(0)
+    try:
+        for ctx in (c, d):
+            ctx.load_scene(S.default_scene()); ctx.set_seeds(seed, seed); ctx.set_image_size(W, H)
+        got = c.render_frames(cams, refl)
+        for i in range(2):
+            cases.assert_parity(got[i], want[i], "wrap frame %d" % i)
+        assert c.get_seeds()[0] == int(o.seeds[0])
+        d.skip_samples(W * H)
+        late = d.render_frames(cams[1:], refl)
+        assert np.array_equal(late[0], got[1])
+        assert d.get_seeds()[0] == c.get_seeds()[0]
+    finally:
+        c.close(); d.close()
