@@ -696,8 +696,11 @@ __device__ V3 traceSample(const SceneView & sc, V3 origin, V3 ray, int reflNumbe
 #ifndef RFX_BIG_THREADS
 #define RFX_BIG_THREADS 128
 #endif
+#ifndef RFX_BIG_SMEM_SCENE
+#define RFX_BIG_SMEM_SCENE 0
+#endif
 #ifndef RFX_BIG_MINBLOCKS
-#define RFX_BIG_MINBLOCKS 1
+#define RFX_BIG_MINBLOCKS 8      // 64 registers: the BVH walk is latency-bound, resident warps matter more than spills (profiles/README.md)
 #endif
 constexpr int TRACE_THREADS = RFX_BIG_THREADS;
 
@@ -705,8 +708,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, RFX_BIG_MINBLOCKS) k_trace(cons
                                                          const __grid_constant__ FrameParams fp,
                                                          const uint32_t * __restrict__ sampleStates, float * __restrict__ image,
                                                          uint32_t * __restrict__ argbOut, uint32_t * __restrict__ sigOut,
-                                                         unsigned long long * __restrict__ counters)
+                                                         unsigned long long * __restrict__ counters, int tiled)
 {
+#if RFX_BIG_SMEM_SCENE
   extern __shared__ uint4 smemBlob[];
   {
     const uint4 * src = reinterpret_cast<const uint4 *>(sceneBlob);
@@ -714,6 +718,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, RFX_BIG_MINBLOCKS) k_trace(cons
   }
   __syncthreads();
   const SceneView sc = makeView(reinterpret_cast<const unsigned char *>(smemBlob));
+#else
+  // the blob is read in place: 1024 spheres are 16 KB of float4 that stay in L1 (copying 60 KB into every CTA's shared memory
+  // cost more than the loads it saved, profiles/README.md)
+  const SceneView sc = makeView(sceneBlob);
+#endif
 
   uint32_t nBounces = 0, nShadow = 0;
   const V3 eye = mk(fp.eye[0], fp.eye[1], fp.eye[2]);
@@ -721,8 +730,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, RFX_BIG_MINBLOCKS) k_trace(cons
 
   if (fp.sampleNum > 0)
   {
-    const uint64_t p = fp.p0 + gid;
-    if (p < fp.p1)
+    // row-aligned slices (whole frames, bands): warps own 4x8 pixel tiles, so the rays of a warp walk the same BVH nodes;
+    // any other slice: 32 consecutive pixels of the scan order
+    uint64_t p = fp.p0 + gid;
+    bool inside = p < fp.p1;
+    if (tiled)
+    {
+      const uint32_t tilesX = (fp.W + 3u) / 4u;
+      const uint32_t warp = (uint32_t)(gid >> 5), lane = threadIdx.x & 31u;
+      const uint32_t x = (warp % tilesX) * 4u + (lane & 3u);
+      const uint32_t y = (uint32_t)(fp.p0 / fp.W) + (warp / tilesX) * 8u + (lane >> 2);
+      p = (uint64_t)y * fp.W + x;
+      inside = x < fp.W && p < fp.p1;
+    }
+    if (inside)
     {
       const uint32_t y = (uint32_t)(p / fp.W), x = (uint32_t)(p % fp.W);
       const int sn = fp.sampleNum;
@@ -731,13 +752,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, RFX_BIG_MINBLOCKS) k_trace(cons
       float rndx = 0, rndy = 0;
       if (fp.jitter)
       {
-        uint32_t s = lcgJump(fp.seedRender, (uint32_t)(2 * gid));      // two draws per pixel, Render.cpp:177-178
+        uint32_t s = lcgJump(fp.seedRender, (uint32_t)(2 * (p - fp.p0)));   // two draws per pixel, Render.cpp:177-178
         s = 214013u * s + 2531011u; rndx = divExact(float((int)((s >> 16) & 0x7FFFu)), 32767.0f, RFX_RCP_32767);
         s = 214013u * s + 2531011u; rndy = divExact(float((int)((s >> 16) & 0x7FFFu)), 32767.0f, RFX_RCP_32767);
       }
       V3 fin = mk(0.0f, 0.0f, 0.0f);
       uint32_t sig = 2166136261u;
-      const uint32_t * st = sampleStates + gid * (uint64_t)(sn * sn);
+      const uint32_t * st = sampleStates + (p - fp.p0) * (uint64_t)(sn * sn);
       for (int ssx = 0; ssx < sn; ssx++)
         for (int ssy = 0; ssy < sn; ssy++)
         {
@@ -810,8 +831,17 @@ int launchTrace(const TraceWork & w, cudaStream_t st)
 {
   const FrameParams & fp = w.fp;
   uint64_t nThreads;
+  int tiled = 0;
   if (fp.sampleNum > 0)
+  {
     nThreads = fp.p1 - fp.p0;
+    if (fp.p0 % fp.W == 0 && fp.p1 % fp.W == 0)
+    {
+      tiled = 1;
+      const uint64_t rows = (fp.p1 - fp.p0) / fp.W;
+      nThreads = (uint64_t)((fp.W + 3u) / 4u) * ((rows + 7u) / 8u) * 32u;
+    }
+  }
   else
   {
     // block origins in [p0, p1): the host computed firstRank; count = originsBefore(p1) - firstRank is passed via p1 bound
@@ -820,7 +850,7 @@ int launchTrace(const TraceWork & w, cudaStream_t st)
     nThreads = (uint64_t)bw * bh - fp.firstRank;   // upper bound; threads past p1 exit
   }
   if (nThreads == 0) return 0;
-  const uint32_t smem = (w.sceneBytes + 15u) & ~15u;
+  const uint32_t smem = RFX_BIG_SMEM_SCENE ? ((w.sceneBytes + 15u) & ~15u) : 0u;
   static uint32_t smemOptedIn = 0;
   if (smem > 48 * 1024 && smem > smemOptedIn)
   {
@@ -829,7 +859,7 @@ int launchTrace(const TraceWork & w, cudaStream_t st)
   }
   const uint32_t blocks = (uint32_t)((nThreads + TRACE_THREADS - 1) / TRACE_THREADS);
   k_trace<<<blocks, TRACE_THREADS, smem, st>>>(reinterpret_cast<const unsigned char *>(w.sceneBlob), smem, fp, w.sampleStates,
-                                               w.image, w.argbOut, w.sigOut, w.counters);
+                                               w.image, w.argbOut, w.sigOut, w.counters, tiled);
   return 1;
 }
 
