@@ -153,10 +153,10 @@ RFX_API int rfx_synchronize(rfx_ctx * ctx);
 RFX_API int rfx_get_stats(rfx_ctx * ctx, rfx_stats * out);     /* synchronises */
 RFX_API int rfx_stats_reset(rfx_ctx * ctx);
 RFX_API int rfx_enable_profiling(rfx_ctx * ctx, int on);
-/* kernel selection: 0 = automatic (constant-bank kernel when the scene fits, shared-memory kernel otherwise),
- * 1 = constant-bank kernel if it fits, 2 = always the shared-memory kernel.  Results are identical; tests use it. */
+/* kernel selection: 0 = automatic (constant-bank kernel when the scene fits, the general blob kernel otherwise),
+ * 1 = constant-bank kernel if it fits, 2 = always the general blob kernel.  Results are identical; tests use it. */
 RFX_API int rfx_force_path(rfx_ctx * ctx, int path);
-/* acceleration structure of the shared-memory kernel: 0 = automatic (bounding-volume hierarchy over the spheres when there are
+/* acceleration structure of the general blob kernel: 0 = automatic (bounding-volume hierarchy over the spheres when there are
  * more than 32), 1 = always, 2 = never (the reference's brute-force list walk).  Results are identical; tests compare them. */
 RFX_API int rfx_set_bvh_mode(rfx_ctx * ctx, int mode);
 /* cost-ordered tile scheduling of the constant-bank fast kernel: every launch records which tiles held long paths and the next

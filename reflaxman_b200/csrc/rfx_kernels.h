@@ -76,7 +76,7 @@ struct TraceWork
   unsigned long long * counters;// device [32][2] striped {bounces, shadowRays}
   TileOrder order;              // fast constant-bank kernel only
 };
-int launchTrace(const TraceWork & w, cudaStream_t st);                              // any scene: shared-memory resident blob
+int launchTrace(const TraceWork & w, cudaStream_t st);                              // any scene: blob in global memory, BVH over the spheres
 // small scenes: constant-bank resident; *fastGrid (optional) receives the CTA count of the fast kernel's grid, 0 when the
 // general kernel ran (the caller keeps tile-order history only for fast launches)
 int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st, uint32_t * fastGrid = nullptr);

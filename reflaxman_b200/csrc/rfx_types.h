@@ -1,6 +1,6 @@
 // rfx_types.h — POD records shared by the host flattening code (rfx_capi.cu) and the sm_100a kernels (rfx_kernels.cu).
 //
-// HBM layout of a scene ("scene blob", one contiguous allocation, copied into shared memory by every CTA):
+// HBM layout of a scene ("scene blob", one contiguous allocation, read in place by k_trace):
 //   SceneHeader | Light[nLights] | float4 sphere[nSpheres] (cx,cy,cz,r^2) | Triangle[nTris] | Plane[nPlanes] |
 //   Material[nObjects] (sorted order: spheres, triangles, planes) | TexRef[nTextures]
 // Objects are grouped by kind so the intersection loops are branch-free over a homogeneous array; every record keeps
