@@ -20,10 +20,10 @@ def capi(rfx_lib):
     return capi
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["constbank", "smem"])
+@pytest.mark.parametrize("path", [1, 2], ids=["constbank", "blob"])
 @pytest.mark.parametrize("name", cases.GOLDEN)
 def test_gpu_matches_golden(capi, name, path):
-    """both K2 variants: 1 = constant-bank kernel (small scenes), 2 = shared-memory kernel (any scene)"""
+    """both K2 variants: 1 = constant-bank kernel (small scenes), 2 = general blob kernel (any scene)"""
     g = cases.load_golden(name)
     eng = cases.GpuEngine(capi, g["scene"], g["W"], g["H"], g["seed"])
     eng.c.force_path(path)
@@ -55,7 +55,7 @@ def test_render_next_slicing_is_invisible(capi, chunk):
         a.close(); b.close()
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["constbank", "smem"])
+@pytest.mark.parametrize("path", [1, 2], ids=["constbank", "blob"])
 def test_signatures_and_rays_match_oracle_config1(capi, oracle, path):
     """config 1 (1024x768, depth 20): identical hit paths on 100 % of pixels, identical ray count, parity bar met."""
     W, H = 1024, 768
@@ -141,7 +141,7 @@ def test_error_behaviour(capi):
 
 @pytest.mark.parametrize("n_side,size,depth", [(6, (128, 72), 8), (12, (160, 90), 6), (32, (96, 54), 4)])
 def test_bvh_equals_brute_force(capi, oracle, n_side, size, depth):
-    """SURVEY f-3: the bounding-volume hierarchy of the shared-memory kernel only selects which spheres get the exact test;
+    """SURVEY f-3: the bounding-volume hierarchy of the general blob kernel only selects which spheres get the exact test;
     the float image, the hit-path signatures and the ray counts must be IDENTICAL to the brute-force list walk, and both
     must meet the parity bar against the oracle."""
     W, H = size
@@ -187,7 +187,7 @@ def _mixed_scene():
 
 
 def test_mixed_scene_all_kernels_match_oracle(capi, oracle):
-    """fast kernel (ARGB batch path), general constant-bank kernel and shared-memory kernel on a scene with several lights
+    """fast kernel (ARGB batch path), general constant-bank kernel and blob kernel on a scene with several lights
     and every object kind: identical hit paths and ray counts to the oracle, identical images to each other."""
     W, H, refl, seed = 250, 131, 12, 4242
     cam = S.orbit_cameras(7)[2]
