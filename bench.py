@@ -62,7 +62,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -240,7 +240,6 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     ms = maxreduce(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
     st = ctx.stats()
     rays_total = sumreduce(float(st["rays"]))
     launches = st["kernel_launches"]
@@ -271,6 +270,7 @@ def run_ours(args):
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = maxreduce(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (device-resident arm and end-to-end arm)
     if world > 1:
         dist.barrier()
     st2 = ctx.stats()
