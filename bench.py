@@ -40,7 +40,7 @@ METRIC = "Mrays/s at 1920x1080, default scene, reflection depth 20 (frames/s alo
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
@@ -51,18 +51,21 @@ def parse():
 
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions (B200_PROFILING.md's clocks line).  The sampler
+    starts before the warm-up (nvidia-smi needs ~0.2 s to produce its first line); only the lines whose timestamp falls
+    inside a window opened by begin() and closed by end() are used."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
         self.rows = []
+        self.windows = []
         self.p = None
         self.idx = gpu_index
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -71,12 +74,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def begin(self):
+        self.windows.append([time.time(), None])
+
+    def end(self):
+        self.windows[-1][1] = time.time()
 
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.p.terminate()
         try:
             self.p.wait(timeout=2)
@@ -84,20 +93,28 @@ class ClockSampler:
             self.p.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        import datetime
+        for t, r in self.rows:
             c = [x.strip() for x in r.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
+                continue
+            try:   # nvidia-smi's own timestamp (local time); the pipe may deliver lines late
+                t = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                pass
+            # a line describes the interval that ended when it was printed: accept it up to one period after a window closed
+            if not any(w0 <= t <= (w1 if w1 is not None else t) + 0.03 for w0, w1 in self.windows):
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
+                sm.append(float(c[2])); mx.append(float(c[3]))
             except ValueError:
                 continue
-            for n, v in zip(names, c[5:9]):
+            for n, v in zip(names, c[6:10]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampled": "nvidia-smi -lms 20, lines inside the two timed regions"}
 
 
 def reference_cpu_run(binary, nproc, frames=1):
@@ -184,6 +201,9 @@ def run_ours(args):
 
     F = args.frames
     K, Wm = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     ctx = capi.Context(local)
     scene = S.default_scene()
     ctx.load_scene(scene)
@@ -229,16 +249,15 @@ def run_ours(args):
         ctx.render_frames_device(cams, DEPTH, 1, out_dev.data_ptr(), stream.cuda_stream)
     barrier()
     ctx.stats_reset()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     e0.record(stream)
     for _ in range(K):
         ctx.render_frames_device(cams, DEPTH, 1, out_dev.data_ptr(), stream.cuda_stream)
     e1.record(stream)
     barrier()
+    sampler.end()
     ms = maxreduce(e0.elapsed_time(e1))
     st = ctx.stats()
     rays_total = sumreduce(float(st["rays"]))
@@ -265,12 +284,14 @@ def run_ours(args):
         e2e_step()
     barrier()
     ctx.stats_reset()
+    sampler.begin()
     t0 = time.perf_counter()
     for _ in range(K):
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = maxreduce(time.perf_counter() - t0)
-    clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (device-resident arm and end-to-end arm)
+    sampler.end()
+    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         dist.barrier()
     st2 = ctx.stats()
