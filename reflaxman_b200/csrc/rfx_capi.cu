@@ -461,6 +461,7 @@ int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, boo
       const uint64_t per = (uint64_t)sn * sn;
       uint64_t pix = MAX_CALLS_PER_LAUNCH / per;
       if (pix < 1) pix = 1;
+      if (cur % ctx->W == 0 && pix >= ctx->W) pix -= pix % ctx->W;   // whole rows keep the chunk on the tiled fast kernel
       end = preStates ? p1 : std::min(p1, cur + pix);
       nCalls = (end - cur) * per;
     }

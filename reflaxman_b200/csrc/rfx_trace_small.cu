@@ -37,6 +37,9 @@ namespace rfx
 // cost classes of the tile scheduler: class c holds the tile groups whose longest path has >= bound[c] segments (last class: the rest)
 #define RFX_TILE_BOUNDS { 8u, 4u, 2u }
 #endif
+#ifndef RFX_ANY_MINBLOCKS
+#define RFX_ANY_MINBLOCKS 6        // general kernel (signatures, float image, every mode)
+#endif
 #ifndef RFX_SMALL_THREADS
 #define RFX_SMALL_THREADS 128
 #endif
@@ -449,13 +452,15 @@ __device__ __forceinline__ unsigned long long globalTimer() { unsigned long long
 __device__ __forceinline__ unsigned smId() { unsigned s; asm volatile("mov.u32 %0, %smid;" : "=r"(s)); return s; }
 #endif
 
-// Fast kernel: a row-aligned slice (whole frame, band of rows, or this GPU's strips of a split frame), one sample per
-// pixel, no jitter, ARGB output only.  2-D grid: blockIdx.y = tile row, blockIdx.x * warps + warp = tile column.
-template <int FEAT>
-__global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_small(const __grid_constant__ SmallScene sc, const __grid_constant__ FrameParams fp,
+// Fast kernel: a row-aligned slice (whole frame, band of rows, or this GPU's strips of a split frame).  2-D grid:
+// blockIdx.y = tile row, blockIdx.x * warps + warp = tile column.  MULTI = false: one sample per pixel, no jitter, ARGB
+// output only (the bench path).  MULTI = true: the same tiling and scheduling for grid SSAA (Render.cpp:174-196), additive
+// jitter and accumulation, and the float image of the Render API.
+template <int FEAT, bool MULTI>
+__global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS) k_trace_small(const __grid_constant__ SmallScene sc, const __grid_constant__ FrameParams fp,
                                                                const uint32_t * __restrict__ sampleStates, uint32_t * __restrict__ argbOut,
                                                                unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1,
-                                                               const TileOrder ord)
+                                                               const TileOrder ord, float * __restrict__ image)
 {
   // which tile group does this CTA render: index order, or the previous launch's cost order (expensive classes first)
   uint32_t bx = blockIdx.x, by = blockIdx.y;
@@ -489,8 +494,9 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
     y = (k * fp.stripWorld + fp.stripRank) * fp.stripRows + (y % fp.stripRows);
   }
   const bool valid = x < fp.W && y < y1;
-  uint32_t events = 0;
-  if (valid)
+  uint32_t events = 0;                                                   // MULTI: of the longest call in the low half (cost class)
+  uint32_t nBounces = 0, nShadow = 0;                                    // MULTI: totals over the calls
+  if (valid && !MULTI)
   {
     const uint32_t q = y * fp.W + x;                                     // < 2^32 for every frame size the API accepts
     uint32_t s = __ldg(sampleStates + (q - y0 * fp.W));
@@ -508,6 +514,59 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
 #else
     argbOut[q] = packArgb(c.x, c.y, c.z);
 #endif
+    nBounces = events & 0xFFFFu; nShadow = events >> 16;
+  }
+  if (valid && MULTI)
+  {
+    const uint32_t q = y * fp.W + x;
+    const uint32_t rel = q - y0 * fp.W;                                  // pixel index inside the slice
+    const int sn = fp.sampleNum;
+    const int nCalls = sn * sn;
+    const uint32_t * st = sampleStates + (uint64_t)rel * (uint64_t)nCalls;
+    const float rx = float(x) - fp.wHalf;
+    const float ry = float(y) - fp.hHalf;
+    float rndx = 0, rndy = 0;
+    if (fp.jitter)
+    {
+      uint32_t s = lcgJump(fp.seedRender, 2u * rel);                     // two draws per pixel, Render.cpp:177-178
+      s = 214013u * s + 2531011u; rndx = divExact(float((int)((s >> 16) & 0x7FFFu)), 32767.0f, RFX_RCP_32767);
+      s = 214013u * s + 2531011u; rndy = divExact(float((int)((s >> 16) & 0x7FFFu)), 32767.0f, RFX_RCP_32767);
+    }
+    V3 fin = mk(0.0f, 0.0f, 0.0f);
+    int ssx = 0, ssy = 0;
+#pragma unroll 1
+    for (int call = 0; call < nCalls; call++)
+    {
+      uint32_t s = __ldg(st + call);
+      V3 rd;
+      rngTriple(s, rd.x, rd.y, rd.z);
+      // (rx + float(ssx)/s) + rndx, Render.cpp:184; x / 1.0f == x exactly, so sn == 1 skips the divides
+      const float offx = sn == 1 ? 0.0f : float(ssx) / float(sn);
+      const float offy = sn == 1 ? 0.0f : float(ssy) / float(sn);
+      const float px = (rx + offx) + rndx;
+      const float py = (ry + offy) + rndy;
+      const V3 ray = mk((px * fp.view[0] + py * fp.view[1]) + fp.rz * fp.view[2],
+                        (px * fp.view[3] + py * fp.view[4]) + fp.rz * fp.view[5],
+                        (px * fp.view[6] + py * fp.view[7]) + fp.rz * fp.view[8]);
+      uint32_t ev = 0, sig = 0;
+      const V3 c = traceSmall<false, FEAT>(sc, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, ev, sig);
+      fin = vadd(fin, c);
+      nBounces += ev & 0xFFFFu; nShadow += ev >> 16;
+      events = max(events, ev & 0xFFFFu);
+      if (++ssy == sn) { ssy = 0; ssx++; }                  // ssx outer, ssy inner: the reference's summation order
+    }
+    if (sn != 1)   // finColor /= float(s*s): dividing by 1.0f is the identity (Color.cpp:50-61)
+    {
+      const float sq = float(nCalls);
+      fin = mk(fin.x / sq, fin.y / sq, fin.z / sq);
+    }
+    if (image)
+    {
+      float * px = image + (uint64_t)q * 3;
+      if (fp.accumulate) { px[0] = px[0] + fin.x; px[1] = px[1] + fin.y; px[2] = px[2] + fin.z; }
+      else { px[0] = fin.x; px[1] = fin.y; px[2] = fin.z; }
+    }
+    if (argbOut) argbOut[q] = packArgb(fin.x, fin.y, fin.z);
   }
   if (ord.outLists)
   {
@@ -537,12 +596,12 @@ __global__ void __launch_bounds__(SMALL_THREADS, RFX_SMALL_MINBLOCKS) k_trace_sm
     if (id < (1u << 16)) { g_ctaTimes[id][0] = tStart; g_ctaTimes[id][1] = globalTimer(); g_ctaTimes[id][2] = smId(); }
   }
 #endif
-  flushCounters(counters, events & 0xFFFFu, events >> 16, (blockIdx.y * gridDim.x + blockIdx.x) * (SMALL_THREADS / 32) + warp);
+  flushCounters(counters, nBounces, nShadow, (blockIdx.y * gridDim.x + blockIdx.x) * (SMALL_THREADS / 32) + warp);
 }
 
 // General kernel: every mode of Render::renderNext (grid SSAA, block preview, additive jitter, arbitrary pixel slices,
 // float image, signatures).
-__global__ void __launch_bounds__(SMALL_THREADS, 6) k_trace_small_any(const __grid_constant__ SmallScene sc, const __grid_constant__ FrameParams fp,
+__global__ void __launch_bounds__(SMALL_THREADS, RFX_ANY_MINBLOCKS) k_trace_small_any(const __grid_constant__ SmallScene sc, const __grid_constant__ FrameParams fp,
                                                                const uint32_t * __restrict__ sampleStates, float * __restrict__ image,
                                                                uint32_t * __restrict__ argbOut, uint32_t * __restrict__ sigOut,
                                                                unsigned long long * __restrict__ counters, int tiled)
@@ -658,11 +717,12 @@ __global__ void __launch_bounds__(SMALL_THREADS, 6) k_trace_small_any(const __gr
   flushCounters(counters, nBounces, nShadow, blockIdx.x * (SMALL_THREADS / 32) + (threadIdx.x >> 5));
 }
 
-// rows the fast kernel enumerates for this work (0 = does not qualify): whole rows, 1 sample per pixel, ARGB only
+// rows the fast kernel enumerates for this work (0 = does not qualify): whole rows, grid sampling (not block preview), no signatures
 static uint64_t fastRows(const TraceWork & w)
 {
   const FrameParams & fp = w.fp;
-  if (fp.sampleNum != 1 || fp.jitter || w.image || w.sigOut || !w.argbOut || fp.W == 0) return 0;
+  if (fp.sampleNum < 1 || w.sigOut || (!w.argbOut && !w.image) || fp.W == 0) return 0;
+  if ((uint64_t)fp.sampleNum * fp.sampleNum * (fp.p1 - fp.p0) >= (1ull << 32)) return 0;
   if (fp.p0 % fp.W != 0 || fp.p1 % fp.W != 0 || (uint64_t)fp.W * fp.H >= (1ull << 32)) return 0;
   uint64_t rows = (fp.p1 - fp.p0) / fp.W;
   if (fp.stripWorld)
@@ -718,10 +778,16 @@ int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st
         bool texels = false;
         for (int i = 0; i < SMALL_MAX_TEX; i++) texels = texels || sc.tex[i].px != nullptr;
         const bool lean = !texels && sc.nP == 0 && sc.nL <= 1;
-        if (lean)
-          k_trace_small<0><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W), w.order);
+        const bool multi = fp.sampleNum != 1 || fp.jitter || w.image != nullptr;
+        const uint32_t y0 = (uint32_t)(fp.p0 / fp.W), y1 = (uint32_t)(fp.p1 / fp.W);
+        if (lean && !multi)
+          k_trace_small<0, false><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.order, nullptr);
+        else if (!multi)
+          k_trace_small<F_ALL, false><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.order, nullptr);
+        else if (lean)
+          k_trace_small<0, true><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.order, w.image);
         else
-          k_trace_small<F_ALL><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W), w.order);
+          k_trace_small<F_ALL, true><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.order, w.image);
         return 1;
       }
       nThreads = (uint64_t)((fp.W + RFX_TILE_W - 1) / RFX_TILE_W) * ((rows + RFX_TILE_H - 1) / RFX_TILE_H) * 32;
