@@ -496,6 +496,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
   const bool valid = x < fp.W && y < y1;
   uint32_t events = 0;                                                   // MULTI: of the longest call in the low half (cost class)
   uint32_t nBounces = 0, nShadow = 0;                                    // MULTI: totals over the calls
+  uint32_t packed = 0, qOut = 0;
   if (valid && !MULTI)
   {
     const uint32_t q = y * fp.W + x;                                     // < 2^32 for every frame size the API accepts
@@ -510,11 +511,25 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
     uint32_t sig = 0;
     const V3 c = traceSmall<false, FEAT>(sc, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, events, sig);
 #ifdef RFX_DEBUG_DEPTH
-    argbOut[q] = events;       // debug build (tools/depth_stats.py): bounce-loop iterations | shadow rays << 16 instead of the colour
+    packed = events;           // debug build (tools/depth_stats.py): bounce-loop iterations | shadow rays << 16 instead of the colour
 #else
-    argbOut[q] = packArgb(c.x, c.y, c.z);
+    packed = packArgb(c.x, c.y, c.z);
 #endif
+    qOut = q;
     nBounces = events & 0xFFFFu; nShadow = events >> 16;
+  }
+  if (!MULTI)
+  {
+    // framebuffer store: the four lanes of a tile row hold four consecutive pixels; the first of them stores all four as one
+    // 128-bit word (16-byte aligned when W is a multiple of 4), so a warp writes its 4x8 tile with 8 STG.128
+    const uint32_t p1 = __shfl_down_sync(0xffffffffu, packed, 1), p2 = __shfl_down_sync(0xffffffffu, packed, 2), p3 = __shfl_down_sync(0xffffffffu, packed, 3);
+    const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
+    const bool rowOfFour = RFX_TILE_W % 4u == 0u && (fp.W & 3u) == 0u && ((validMask >> (lane & ~3u)) & 0xFu) == 0xFu;
+    if (rowOfFour)
+    {
+      if ((lane & 3u) == 0u) *reinterpret_cast<uint4 *>(argbOut + qOut) = make_uint4(packed, p1, p2, p3);
+    }
+    else if (valid) argbOut[qOut] = packed;
   }
   if (valid && MULTI)
   {

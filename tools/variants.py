@@ -11,9 +11,7 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 
 VARIANTS = {
     # name: (defines, force_path)
-    "t128_mb8": (["RFX_SMALL_MINBLOCKS=8"], 1),
-    "t128_mb9": (["RFX_SMALL_MINBLOCKS=9"], 1),
-    "t64_mb18": (["RFX_SMALL_THREADS=64", "RFX_SMALL_MINBLOCKS=18"], 1),
+    "base": ([], 1),
 }
 
 
