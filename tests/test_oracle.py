@@ -124,3 +124,71 @@ def test_constant_division_is_exact():
             q0 = rn32(rf * c)
             rem = rn32(rf - q0 * D)
             assert rn32(q0 + rem * c) == rn32(rf / D), (D, r)
+
+
+def test_rand_dirs_cycle_table_model(oracle):
+    """The formulation K1 implements on the GPU (rfx_kernels.cu): the accept flag of a triple depends only on its start position
+    on the LCG's 2^32-state cycle, the position of a seed follows from a bitwise discrete logarithm, and the stream visits
+    positions p0, p0+3, ... in residue class p0 mod 3 until it wraps into the next class (0 -> 2 -> 1 -> 0).  Checked against
+    the oracle's serial stream for a seed just before the wrap (all three classes) and an ordinary one."""
+    A, C, M = 214013, 2531011, 1 << 32
+
+    def jump(s, n):
+        a, c = A, C
+        while n:
+            if n & 1:
+                s = (a * s + c) % M
+            c = (c * (a + 1)) % M
+            a = (a * a) % M
+            n >>= 1
+        return s
+
+    pow2 = []
+    for k in range(32):
+        c = jump(0, 1 << k)
+        pow2.append(((jump(1, 1 << k) - c) % M, c))
+
+    def position(s):                       # k_rng_locate's discrete logarithm
+        pos, t = 0, 0
+        for k in range(32):
+            if ((t ^ s) >> k) & 1:
+                a, c = pow2[k]
+                t = (a * t + c) % M
+                pos |= 1 << k
+        assert t == s
+        return pos
+
+    def accept_at(p):                      # accept flag and states of the triple that starts at cycle position p
+        s0 = jump(0, p % M)
+        st = [s0]
+        for _ in range(3):
+            st.append((A * st[-1] + C) % M)
+        r = ((np.array(st[1:], np.uint32) >> 16) & 0x7FFF).astype(np.float32)
+        v = r / np.float32(16383.5) - np.float32(1.0)
+        sq = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]
+        return (not sq > np.float32(1.0)), s0, st[3], v
+
+    for p0 in (M - 601, M - 602, M - 603, 123456789):
+        seed = jump(0, p0)
+        assert position(seed) == p0
+        n = 300
+        dirs, end_state = oracle.rand_dirs(seed, n)
+        cls_seq = []
+        got, end, p = [], None, p0
+        while len(got) < n:
+            acc, _, after, v = accept_at(p)
+            cls_seq.append(p % 3)
+            if acc:
+                got.append(v)
+                end = after
+            p += 3
+            if p >= M:
+                p -= M                     # the wrapped position lands in the next residue class
+        assert np.array_equal(np.array(got, np.float32).view(np.uint32), dirs.view(np.uint32)), p0
+        assert end == end_state
+        changes = [i for i in range(1, len(cls_seq)) if cls_seq[i] != cls_seq[i - 1]]
+        if p0 > M - 1000:
+            r0 = p0 % 3
+            assert len(changes) == 1 and cls_seq[-1] == (2 if r0 == 0 else r0 - 1)
+        else:
+            assert not changes
