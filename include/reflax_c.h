@@ -66,7 +66,8 @@ typedef struct rfx_device_info
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
 /* Render::Render / ~Render (reference Render.cpp:5-23).  device = CUDA ordinal.  The context starts EMPTY (no
- * default scene): the shim's Render::loadScene issues the reference's scene through the calls below. */
+ * default scene): the shim's Render::loadScene issues the reference's scene through the calls below.
+ * Creation builds the accept-count table of the random stream's LCG cycle on the device (about 5 ms, 8.4 MB). */
 RFX_API int rfx_create(rfx_ctx ** out, int device);
 RFX_API void rfx_destroy(rfx_ctx * ctx);
 RFX_API const char * rfx_last_error(const rfx_ctx * ctx);       /* ctx may be NULL: last rfx_create failure */
@@ -99,7 +100,9 @@ RFX_API int rfx_set_camera(rfx_ctx * ctx, const float eye[3], const float view[9
  * (Render.cpp:177-178).  Both streams continue across frames exactly as in one reference process. ----------- */
 RFX_API int rfx_set_seeds(rfx_ctx * ctx, uint32_t seed_vector3, uint32_t seed_render);
 RFX_API int rfx_get_seeds(rfx_ctx * ctx, uint32_t out[2]);            /* current LCG states (synchronises) */
-RFX_API int rfx_skip_samples(rfx_ctx * ctx, uint64_t n_trace_calls);  /* advance the randDir stream as if n Scene::trace calls had run (frame sharding) */
+/* advance the randDir stream as if n Scene::trace calls had run (frame sharding).  The stream's accept pattern is tabulated
+ * over the LCG's whole 2^32-state cycle at rfx_create, so the cost does not depend on n: one small kernel. */
+RFX_API int rfx_skip_samples(rfx_ctx * ctx, uint64_t n_trace_calls);
 
 /* ---- Render (reference Render.h:30-41) ----------------------------------------------------------------- */
 RFX_API int rfx_set_image_size(rfx_ctx * ctx, uint32_t width, uint32_t height);   /* Render::setImageSize, Render.cpp:57-80 */

@@ -466,17 +466,20 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
   uint32_t bx = blockIdx.x, by = blockIdx.y;
   if (ord.inLists)
   {
-    uint32_t b = blockIdx.y * gridDim.x + blockIdx.x;
-    int c = 0;
+    uint32_t total = 0;
 #pragma unroll
-    for (; c < TILE_CLASSES - 1; c++)
+    for (int c = 0; c < TILE_CLASSES; c++) total += ord.inCounts[c];
+    if (total == gridDim.x * gridDim.y)      // the lists are a permutation of this grid (always, unless the recording launch failed)
     {
-      const uint32_t n = ord.inCounts[c];
-      if (b < n) break;
-      b -= n;
-    }
-    if (b < ord.inCounts[c])
-    {
+      uint32_t b = blockIdx.y * gridDim.x + blockIdx.x;
+      int c = 0;
+#pragma unroll
+      for (; c < TILE_CLASSES - 1; c++)
+      {
+        const uint32_t n = ord.inCounts[c];
+        if (b < n) break;
+        b -= n;
+      }
       const uint32_t packed = ord.inLists[(uint32_t)c * ord.capacity + b];
       bx = packed & 0xFFFFu; by = packed >> 16;
     }
