@@ -3,16 +3,21 @@
 //
 // Design (B200, FP32 CUDA cores; this path has no dense contraction, so no tensor cores):
 //   * The whole scene travels as a __grid_constant__ kernel parameter: every sphere/triangle coefficient is a
-//     constant-bank operand — no global loads, no address arithmetic in the test loops.
+//     constant-bank operand — no global or shared loads in the test loops.
 //   * ONE intersection call site.  Scene::trace is a state machine per lane: the query in flight is either the bounce
 //     segment (closest hit) or the shadow ray of light `li` (any hit); lanes in either state share the same pass over
-//     the objects.  That halves the code of the kernel (the instruction working set now fits the 32 KB L1.5
-//     instruction cache) and keeps lanes of a warp that sit in different phases busy in the same loop.
-//   * The pass over the objects is one rolled loop per kind: the branch-free reject test (sphere discriminant and ray
-//     side, triangle plane side) followed, for the lanes that pass it, by the sqrt/divide tail.
-//   * Warps own 4x8 pixel tiles (coherent primary/secondary rays; 8x4, 16x2, 32x1 measured slower); the fast kernel
-//     (whole rows, 1 sample per pixel, ARGB only) uses a 2-D grid so that no thread executes an integer division.
+//     the objects.  That halves the code of the kernel (it fits the 32 KB L1.5 instruction cache) and keeps lanes of a
+//     warp that sit in different phases busy in the same loops.
+//   * The pass over the objects: four spheres per trip — the reference's discriminant expression, 17 un-fused FP32 ops
+//     per sphere, the FP32 pipe is the limit there — behind ONE divergent gate region for their sqrt/divide tails; then
+//     the triangles (plane-side test on sign bits, tail with the divide); planes last.
+//   * Warps own 4x8 pixel tiles of a 2-D grid (no integer division per thread); tiles are started in the cost order the
+//     previous launch recorded (TileOrder: long paths first), which removes the ~45 us drain behind the mirror-sphere tiles.
+//   * 128-thread CTAs, 63 registers, 8 CTAs per SM; the frame is written with one 128-bit store per tile row.
+//   * The same kernel (MULTI instantiation) serves row-aligned SSAA / additive / float-image slices of the Render API;
+//     k_trace_small_any keeps the arbitrary pixel slices, block preview and signature runs.
 //   * The bounce recursion is the reference's own bounded iterative loop carrying throughput (mulColor).
+// Every step above was measured; profiles/README.md has the numbers, including the experiments that were not kept.
 //
 // ARITHMETIC CONTRACT: compiled with --fmad=false, no fast-math: every + - * / sqrtf is the IEEE binary32 RN
 // operation, in the reference's evaluation order.  Hoisting a per-ray invariant (|ray|^2,
