@@ -11,6 +11,9 @@
 namespace rfx
 {
 
+#ifndef RFX_TEXEL_LUT
+#define RFX_TEXEL_LUT 0
+#endif
 #define RFX_VSN 1.08420217248550443e-19f   // sqrtf(FLT_MIN) = 2^-63, reference trace_math.h:17
 #define RFX_DELTA 0.0001f                  // reference trace_math.h:18
 
@@ -43,6 +46,7 @@ __device__ __forceinline__ float divExact(float r, float D, float rcpD)
 }
 #define RFX_RCP_16383_5 6.103701889514923e-05f   // RN(1 / 16383.5)
 #define RFX_RCP_32767 3.0518509447574615e-05f    // RN(1 / 32767)
+#define RFX_RCP_255 0.003921568859368563f        // RN(1 / 255)
 
 __device__ __forceinline__ float lcgDrawUnit(uint32_t & s)
 {
@@ -171,8 +175,14 @@ __device__ __forceinline__ float clamp01(float v) { return v < 0.0f ? 0.0f : v >
 __device__ __forceinline__ V3 texel(const TexRef & t, const float * __restrict__ lut, uint32_t x, uint32_t y)
 {
   const uint32_t c = __ldg(t.px + (x + t.w * y));
-  // Color(ARGB): float(byte) / 255.0f (Color.cpp:11-13) through the host-computed 256-entry table
-  return mk(__ldg(lut + ((c >> 16) & 0xFFu)), __ldg(lut + ((c >> 8) & 0xFFu)), __ldg(lut + (c & 0xFFu)));
+  // Color(ARGB): float(byte) / 255.0f (Color.cpp:11-13)
+#if RFX_TEXEL_LUT
+  return mk(__ldg(lut + ((c >> 16) & 0xFFu)), __ldg(lut + ((c >> 8) & 0xFFu)), __ldg(lut + (c & 0xFFu)));   // host-computed 256-entry table
+#else
+  // the exact three-instruction constant division (divExact, proven for every byte) instead of three dependent table loads
+  return mk(divExact(float((c >> 16) & 0xFFu), 255.0f, RFX_RCP_255), divExact(float((c >> 8) & 0xFFu), 255.0f, RFX_RCP_255),
+            divExact(float(c & 0xFFu), 255.0f, RFX_RCP_255));
+#endif
 }
 
 // non-empty texture, (u, v) already known to lie in [0, 1]: Texture.cpp:246-268

@@ -116,7 +116,8 @@ def test_constant_division_is_exact():
             n += 1
         return sgn * n * ulp
 
-    for D, hi, c_src in ((Fraction(32767, 2), 32768, 6.103701889514923e-05), (Fraction(32767), 32768, 3.0518509447574615e-05)):
+    for D, hi, c_src in ((Fraction(32767, 2), 32768, 6.103701889514923e-05), (Fraction(32767), 32768, 3.0518509447574615e-05),
+                         (Fraction(255), 256, 0.003921568859368563)):
         c = rn32(1 / D)
         assert float(c) == float(np.float32(c_src))          # the literal in rfx_device.cuh is RN(1/D)
         for r in range(hi):
