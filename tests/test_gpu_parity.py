@@ -300,3 +300,28 @@ def test_random_stream_across_the_lcg_cycle_wrap(capi, oracle, back):
         assert d.get_seeds()[0] == c.get_seeds()[0]
     finally:
         c.close(); d.close()
+
+
+def test_stream_skip_matches_serial_stream(capi, oracle):
+    """rfx_skip_samples finds the end of the skipped stretch in the table of the LCG cycle (one small kernel whatever n is):
+    the resulting stream state equals the oracle's serial walk, skips compose, and a skip longer than a whole residue class
+    of the cycle (chunked by the host) equals the same distance in pieces."""
+    seed = 20260101
+    n = 3_000_000
+    _, end_state = oracle.rand_dirs(seed, n)
+    c = capi.Context(0)
+    d = capi.Context(0)
+    try:
+        c.set_seeds(seed, 1); d.set_seeds(seed, 1)
+        c.skip_samples(n)
+        assert c.get_seeds()[0] == end_state
+        for part in (1, 999_999, 2_000_000):
+            d.skip_samples(part)
+        assert d.get_seeds()[0] == end_state
+        big = 1_700_000_000                       # > 0.75e9 accepted triples of one residue class: crosses the cycle wrap at least twice
+        c.skip_samples(big)
+        for _ in range(17):
+            d.skip_samples(100_000_000)
+        assert c.get_seeds()[0] == d.get_seeds()[0]
+    finally:
+        c.close(); d.close()
