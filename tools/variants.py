@@ -11,10 +11,7 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 
 VARIANTS = {
     # name: (defines, force_path)
-    "t128_mb8": ([], 1),
-    "t32_mb32": (["RFX_SMALL_THREADS=32", "RFX_SMALL_MINBLOCKS=32"], 1),
-    "t32_mb28": (["RFX_SMALL_THREADS=32", "RFX_SMALL_MINBLOCKS=28"], 1),
-    "t64_mb16": (["RFX_SMALL_THREADS=64", "RFX_SMALL_MINBLOCKS=16"], 1),
+    "base": ([], 1),
 }
 
 
