@@ -1,7 +1,7 @@
 // rfx_kernels.cu — hand-written sm_100a kernels for ReflaxMan's per-pixel trace-and-shade path.
 //
-//   K1  k_rng_count / k_rng_scan / k_rng_scatter   the serial rejection-sampled LCG stream, ranked in parallel
-//   K2  k_trace                                     primary rays + bounded bounce loop + shadow rays + shading + textures
+//   K1  k_rng_table / k_rng_prefix (once), k_rng_locate / k_rng_rank   the serial rejection-sampled LCG stream, ranked from a table of its cycle
+//   K2  k_trace (any scene; small scenes: rfx_trace_small.cu)   primary rays + bounded bounce loop + shadow rays + shading + textures
 //   K3  k_resolve                                   imagePixel() divide + 8-bit ARGB pack
 //
 // ARITHMETIC CONTRACT.  This file is compiled with --fmad=false and without any fast-math flag: every + - * below
