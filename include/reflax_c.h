@@ -157,7 +157,8 @@ RFX_API int rfx_get_stats(rfx_ctx * ctx, rfx_stats * out);     /* synchronises *
 RFX_API int rfx_stats_reset(rfx_ctx * ctx);
 RFX_API int rfx_enable_profiling(rfx_ctx * ctx, int on);
 /* kernel selection: 0 = automatic (constant-bank kernel when the scene fits, the general blob kernel otherwise),
- * 1 = constant-bank kernel if it fits, 2 = always the general blob kernel.  Results are identical; tests use it. */
+ * 1 = constant-bank kernel if it fits, 2 = always the blob kernels (batch kernel for row-aligned one-sample ARGB slices, the
+ * general one otherwise), 3 = always the general blob kernel.  Results are identical; tests use it. */
 RFX_API int rfx_force_path(rfx_ctx * ctx, int path);
 /* acceleration structure of the general blob kernel: 0 = automatic (bounding-volume hierarchy over the spheres when there are
  * more than 32), 1 = always, 2 = never (the reference's brute-force list walk).  Results are identical; tests compare them. */

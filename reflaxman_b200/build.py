@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("rfx_kernels.cu", "rfx_trace_small.cu", "rfx_capi.cu")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("rfx_kernels.cu", "rfx_trace_small.cu", "rfx_trace_blob.cu", "rfx_capi.cu")]
 HDR = [os.path.join(HERE, "csrc", f) for f in ("rfx_kernels.h", "rfx_types.h", "rfx_device.cuh")] + [os.path.join(HERE, "..", "include", "reflax_c.h")]
 OUT = os.path.join(HERE, "libreflax_b200.so")
 

@@ -14,6 +14,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <limits>
 #include <algorithm>
 
 using namespace rfx;
@@ -133,10 +134,11 @@ struct rfx_ctx
   bool tileHistory = false;                 // the other set holds the order recorded by the previous launch ...
   uint64_t tileKey[4] = { 0, 0, 0, 0 };     // ... over this grid (image size, row range, strip split)
   bool tileOrdering = true;
-  int forcePath = 0;                        // 0 auto, 1 small (constant bank), 2 big (shared memory) — tests exercise both
+  int forcePath = 0;                        // 0 auto, 1 small (constant bank), 2 blob kernels, 3 blob, general kernel only — tests exercise all
   float * dLut = nullptr;
   float4 * dBvhNodes = nullptr; size_t bvhNodesCap = 0;   // big scenes only (see buildBvh)
   int * dBvhPrims = nullptr; size_t bvhPrimsCap = 0;
+  int bvhDepth = 0;                         // depth of the hierarchy in dBvhNodes (0: none)
   int bvhMode = 0;                          // 0 auto (spheres > 32), 1 always, 2 never — tests compare both
 
   // ---- camera + render state (reference Render.h:9-27)
@@ -266,6 +268,10 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
   h.byteLut = ctx->dLut;
   h.bvhNodes = nullptr;
   h.bvhPrims = nullptr;
+  h.bvhLeafSph = nullptr;
+  h.bvhPairs = nullptr;
+  h.bvhRoot = 0;
+  ctx->bvhDepth = 0;
   const bool wantBvh = ctx->bvhMode == 1 ? !sph.empty() : ctx->bvhMode == 2 ? false : sph.size() > 32;
   if (wantBvh)
   {
@@ -286,15 +292,52 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
     buildBvhRec(nodes, prims, 0, (int)prims.size(), margin, 0, maxDepth);
     if (maxDepth < 30)   // traversal stack is 32 deep; a median split of < 2^30 spheres never gets here
     {
-      std::vector<float4> packed(nodes.size() * 2);
-      std::vector<int> order(prims.size());
+      // leaves are padded to 4 slots: bvhPrims[4 * leaf + k] = sphere index (k < count), and — for the batch kernel, which tests a
+      // whole leaf without indirection — bvhLeafSph[4 * leaf + k] = that sphere's (cx, cy, cz, r^2), NaN in the unused slots
+      size_t nLeaves = 0;
+      for (const BvhNode & n : nodes) nLeaves += n.b < 0;
+      // and — also for the batch kernel — the inner nodes once more with both children's boxes side by side ("pair nodes"):
+      // {lo_a.xyz, ref_a} {hi_a.xyz, ref_b} {lo_b.xyz, -} {hi_b.xyz, -}, ref >= 0: pair node index, ref < 0: ~(first slot of a leaf)
+      const size_t nInner = nodes.size() - nLeaves;
+      std::vector<float4> packed(nodes.size() * 2 + nLeaves * 4 + nInner * 4);
+      std::vector<int> ref(nodes.size());
+      {
+        int inner = 0, lf = 0;
+        for (size_t i = 0; i < nodes.size(); i++) ref[i] = nodes[i].b < 0 ? ~(4 * lf++) : inner++;
+      }
+      std::vector<int> order(nLeaves * 4, -1);
+      const float qnan = std::numeric_limits<float>::quiet_NaN();
+      size_t leaf = 0;
       for (size_t i = 0; i < nodes.size(); i++)
       {
+        int a = nodes[i].a;
+        if (nodes[i].b < 0)
+        {
+          for (int k = 0; k < 4; k++)
+          {
+            float4 s4 = make_float4(qnan, qnan, qnan, qnan);
+            if (k < -nodes[i].b)
+            {
+              const HostObj * o = sph[prims[a + k].index];
+              s4 = make_float4(o->center[0], o->center[1], o->center[2], o->sqRadius);
+              order[4 * leaf + k] = prims[a + k].index;
+            }
+            packed[nodes.size() * 2 + 4 * leaf + k] = s4;
+          }
+          a = (int)(4 * leaf++);
+        }
+        else
+        {
+          const BvhNode & ca = nodes[nodes[i].a], & cb = nodes[nodes[i].b];
+          float4 * w = &packed[nodes.size() * 2 + nLeaves * 4 + 4 * (size_t)ref[i]];
+          w[0] = make_float4(ca.lo[0], ca.lo[1], ca.lo[2], 0.0f); w[1] = make_float4(ca.hi[0], ca.hi[1], ca.hi[2], 0.0f);
+          w[2] = make_float4(cb.lo[0], cb.lo[1], cb.lo[2], 0.0f); w[3] = make_float4(cb.hi[0], cb.hi[1], cb.hi[2], 0.0f);
+          memcpy(&w[0].w, &ref[nodes[i].a], 4); memcpy(&w[1].w, &ref[nodes[i].b], 4);
+        }
         float4 lo4 = make_float4(nodes[i].lo[0], nodes[i].lo[1], nodes[i].lo[2], 0.0f), hi4 = make_float4(nodes[i].hi[0], nodes[i].hi[1], nodes[i].hi[2], 0.0f);
-        memcpy(&lo4.w, &nodes[i].a, 4); memcpy(&hi4.w, &nodes[i].b, 4);
+        memcpy(&lo4.w, &a, 4); memcpy(&hi4.w, &nodes[i].b, 4);
         packed[2 * i] = lo4; packed[2 * i + 1] = hi4;
       }
-      for (size_t i = 0; i < prims.size(); i++) order[i] = prims[i].index;
       int rc;
       if ((rc = ensure(ctx, ctx->dBvhNodes, ctx->bvhNodesCap, packed.size())) != RFX_OK) return rc;
       if ((rc = ensure(ctx, ctx->dBvhPrims, ctx->bvhPrimsCap, order.size())) != RFX_OK) return rc;
@@ -303,7 +346,11 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
       CK(cudaStreamSynchronize(st));
       ctx->stats.h2d_bytes += packed.size() * sizeof(float4) + order.size() * sizeof(int);
       h.bvhNodes = ctx->dBvhNodes;
+      ctx->bvhDepth = maxDepth;
       h.bvhPrims = ctx->dBvhPrims;
+      h.bvhLeafSph = ctx->dBvhNodes + nodes.size() * 2;
+      h.bvhPairs = h.bvhLeafSph + nLeaves * 4;
+      h.bvhRoot = ref[0];
     }
   }
   if (off > 200 * 1024) return fail(ctx, RFX_ERR_ARG, "scene too large for the shared-memory resident layout (200 KB)");
@@ -422,7 +469,7 @@ const uint64_t MAX_CALLS_PER_LAUNCH = 1ull << 25;   // bounds the ranked-state s
 int armTileOrder(rfx_ctx * ctx, TraceWork & w, cudaStream_t st)
 {
   w.order = TileOrder();
-  const uint32_t grid = ctx->smallOk && ctx->forcePath != 2 ? fastGridSize(w) : 0;
+  const uint32_t grid = ctx->smallOk && ctx->forcePath < 2 ? fastGridSize(w) : 0;
   if (!ctx->tileOrdering || grid == 0 || grid > (1u << 22)) { ctx->tileHistory = false; return RFX_OK; }
   const uint64_t key[4] = { ((uint64_t)w.fp.W << 32) | w.fp.H, w.fp.p0, w.fp.p1,
                             ((uint64_t)w.fp.stripRows << 40) | ((uint64_t)w.fp.stripWorld << 20) | w.fp.stripRank };
@@ -494,9 +541,11 @@ int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, boo
         evA = ctx->evPool[ctx->evUsed++]; evB = ctx->evPool[ctx->evUsed++];
         CK(cudaEventRecord(evA, st));
       }
-      const bool useSmall = ctx->forcePath == 1 ? ctx->smallOk : ctx->forcePath == 2 ? false : ctx->smallOk;
+      const bool useSmall = ctx->forcePath >= 2 ? false : ctx->smallOk;
       if (useSmall && (rc = armTileOrder(ctx, w, st)) != RFX_OK) return rc;
-      ctx->stats.kernel_launches += useSmall ? launchTraceSmall(ctx->small, w, st) : launchTrace(w, st);
+      if (useSmall) ctx->stats.kernel_launches += launchTraceSmall(ctx->small, w, st);
+      else if (ctx->forcePath != 3 && launchTraceBlobFast(w, ctx->bvhDepth, st)) ctx->stats.kernel_launches += 1;
+      else ctx->stats.kernel_launches += launchTrace(w, st);
       if (evB) CK(cudaEventRecord(evB, st));
       CK(cudaGetLastError());
       ctx->stats.samples += nCalls;
@@ -914,7 +963,7 @@ int rfx_render_strips(rfx_ctx * ctx, uint32_t strip_rows, uint32_t world, uint32
   if ((rc = useStream(ctx, st)) != RFX_OK) return rc;
   if ((rc = uploadScene(ctx, st)) != RFX_OK) return rc;
   const uint64_t calls = ctx->sampleNum > 0 ? callsIn(ctx, 0, total) : 0;
-  const bool fast = ctx->sampleNum > 0 && ctx->smallOk && ctx->forcePath != 2 && !ctx->snap.jitter && !ctx->sigOn &&
+  const bool fast = ctx->sampleNum > 0 && ctx->smallOk && ctx->forcePath < 2 && !ctx->snap.jitter && !ctx->sigOn &&
                     strip_rows % 8 == 0 && calls <= (1ull << 26);
   if (!fast)
   {
@@ -1293,7 +1342,7 @@ int rfx_stats_reset(rfx_ctx * ctx)
 
 int rfx_force_path(rfx_ctx * ctx, int path)
 {
-  if (!ctx || path < 0 || path > 2) return RFX_ERR_ARG;
+  if (!ctx || path < 0 || path > 3) return RFX_ERR_ARG;
   ctx->forcePath = path;
   return RFX_OK;
 }

@@ -171,6 +171,37 @@ def test_bvh_equals_brute_force(capi, oracle, n_side, size, depth):
         cases.assert_parity(out[1][0][k][1], o.resolve()[1], "bvh frame %d" % k)
 
 
+@pytest.mark.parametrize("which,size,depth,bvh", [("grid6", (128, 72), 8, 1), ("grid12", (161, 90), 6, 0), ("grid12", (160, 91), 6, 2),
+                                                   ("mixed", (250, 131), 12, 0), ("mixed", (64, 40), 12, 1)])
+def test_blob_batch_kernel_equals_general_blob_kernel(capi, oracle, which, size, depth, bvh):
+    """rfx_trace_blob.cu (state machine, shared-memory traversal stack; row-aligned one-sample ARGB slices of blob scenes) against
+    k_trace: identical frames, ray counts and stream position, with and without the hierarchy, widths that are not a multiple of
+    the tile width, heights that are not a multiple of the tile height; and both meet the parity bar against the oracle."""
+    W, H = size
+    scene = _mixed_scene() if which == "mixed" else S.synthetic_scene(int(which[4:]), floor=S.synthetic_texture(64, 64, 3), skybox=S.synthetic_texture(128, 96, 5))
+    cams = [S.default_camera(), S.orbit_cameras(7)[3]]
+    out = {}
+    for path in (2, 3):
+        c = capi.Context(0)
+        try:
+            c.load_scene(scene); c.set_seeds(99, 99); c.set_image_size(W, H)
+            c.force_path(path); c.set_bvh_mode(bvh); c.stats_reset()
+            frames = c.render_frames(cams, depth)
+            st = c.stats()
+            out[path] = (frames.copy(), st["rays"], st["bounces"], c.get_seeds())
+        finally:
+            c.close()
+    assert np.array_equal(out[2][0], out[3][0])
+    assert out[2][1:] == out[3][1:]
+    o = oracle.OracleRender(scene, W, H, seed=99)
+    rays = 0
+    for k, cam in enumerate(cams):
+        o.render(cam, depth)
+        rays += o.counters["rays"]
+        cases.assert_parity(out[2][0][k], o.resolve()[1], "blob batch kernel frame %d" % k)
+    assert out[2][1] == rays
+
+
 def _mixed_scene():
     """Everything the state machine has to get right at once: three lights (one near the scene, one behind most surfaces,
     one with zero power), nine spheres (an odd count: the pairwise sphere loop has a remainder), a vertical wall, a plane

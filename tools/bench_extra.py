@@ -153,6 +153,8 @@ def config4(args):
     ctx.set_image_size(Wd, Hd); ctx.set_seeds(12345, 12345)
     brute = args.frames == 0
     ctx.set_bvh_mode(2 if brute else 0)
+    if os.environ.get("RFX_FORCE_PATH"):
+        ctx.force_path(int(os.environ["RFX_FORCE_PATH"]))   # 3 = general blob kernel only (A/B against the batch kernel)
     out = torch.empty((1, Hd, Wd), dtype=torch.int32, device="cuda")
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
     cam = capi.pack_cameras([S.default_camera()])
