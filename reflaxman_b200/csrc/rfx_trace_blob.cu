@@ -1,5 +1,6 @@
 // rfx_trace_blob.cu — K2 for scenes that do not fit the constant bank (config 4: 1024 spheres), batch path: a row-aligned
-// slice, one sample per pixel, ARGB out.  Everything else about such scenes (SSAA, block preview, slices, signatures) stays
+// slice, one sample per pixel, ARGB and/or float image out.  Everything else about such scenes (SSAA, jitter, block preview,
+// ragged slices, signatures) stays
 // on k_trace (rfx_kernels.cu), whose results this kernel reproduces bit for bit.
 //
 // It is the structure of the constant-bank kernel (rfx_trace_small.cu) applied to the scene blob in global memory:
@@ -491,7 +492,8 @@ __device__ __forceinline__ V3 traceBlob(const BlobView & sc, int * __restrict__ 
 
 __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob(const unsigned char * __restrict__ sceneBlob, const __grid_constant__ FrameParams fp,
                                                                 const uint32_t * __restrict__ sampleStates, uint32_t * __restrict__ argbOut,
-                                                                unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1)
+                                                                unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1,
+                                                                float * __restrict__ image)
 {
   __shared__ int stackMem[BLOB_STACK * BLOB_THREADS];
   const BlobView sc = blobView(sceneBlob);
@@ -514,7 +516,15 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
     const V3 c = traceBlob(sc, stackMem + threadIdx.x, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, events);
     packed = packArgb(c.x, c.y, c.z);
     qOut = q;
+    if (image)                                                           // Render.cpp:196-207, one sample: colour / 1 == colour
+    {
+      float * px = image + (size_t)q * 3;
+      if (fp.accumulate) { px[0] = px[0] + c.x; px[1] = px[1] + c.y; px[2] = px[2] + c.z; }
+      else { px[0] = c.x; px[1] = c.y; px[2] = c.z; }
+    }
   }
+  if (!argbOut) goto count;
+  {
   // framebuffer: one 128-bit store per tile row (see k_trace_small)
   const uint32_t p1 = __shfl_down_sync(0xffffffffu, packed, 1), p2 = __shfl_down_sync(0xffffffffu, packed, 2), p3 = __shfl_down_sync(0xffffffffu, packed, 3);
   const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
@@ -523,7 +533,9 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
     if ((lane & 3u) == 0u) *reinterpret_cast<uint4 *>(argbOut + qOut) = make_uint4(packed, p1, p2, p3);
   }
   else if (valid) argbOut[qOut] = packed;
+  }
 
+count:
   if (counters)
   {
     const uint32_t wb = __reduce_add_sync(0xffffffffu, events & 0xFFFFu);
@@ -543,7 +555,7 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
 int launchTraceBlobFast(const TraceWork & w, int bvhDepth, cudaStream_t st)
 {
   const FrameParams & fp = w.fp;
-  if (fp.sampleNum != 1 || fp.jitter || w.image || w.sigOut || !w.argbOut || fp.W == 0 || fp.stripWorld) return 0;
+  if (fp.sampleNum != 1 || fp.jitter || w.sigOut || (!w.argbOut && !w.image) || fp.W == 0 || fp.stripWorld) return 0;
   if (fp.p0 % fp.W != 0 || fp.p1 % fp.W != 0 || (uint64_t)fp.W * fp.H >= (1ull << 32)) return 0;
   if (bvhDepth > BLOB_STACK - 2) return 0;
   const uint64_t rows = (fp.p1 - fp.p0) / fp.W;
@@ -551,7 +563,7 @@ int launchTraceBlobFast(const TraceWork & w, int bvhDepth, cudaStream_t st)
   const uint32_t tilesX = (fp.W + 3u) / 4u, warps = BLOB_THREADS / 32;
   const dim3 grid((tilesX + warps - 1) / warps, (uint32_t)((rows + 7) / 8));
   k_trace_blob<<<grid, BLOB_THREADS, 0, st>>>(reinterpret_cast<const unsigned char *>(w.sceneBlob), fp, w.sampleStates, w.argbOut, w.counters,
-                                             (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W));
+                                             (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W), w.image);
   return 1;
 }
 

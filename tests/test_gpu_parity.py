@@ -202,6 +202,27 @@ def test_blob_batch_kernel_equals_general_blob_kernel(capi, oracle, which, size,
     assert out[2][1] == rays
 
 
+def test_blob_batch_kernel_float_image_equals_general_blob_kernel(capi):
+    """Render API (float image) on a blob scene: whole frames and row-aligned chunks go to rfx_trace_blob.cu, ragged chunks to k_trace;
+    the float images are bit-identical to k_trace rendering everything."""
+    W, H, depth = 136, 75, 6
+    scene = S.synthetic_scene(8, floor=S.synthetic_texture(64, 64, 3), skybox=S.synthetic_texture(128, 96, 5))
+    cam = S.orbit_cameras(5)[1]
+    out = {}
+    for path, chunk in ((3, None), (2, None), (2, W * 16), (2, 1000)):
+        c = capi.Context(0)
+        try:
+            c.load_scene(scene); c.set_seeds(5, 5); c.set_image_size(W, H)
+            c.force_path(path); c.set_bvh_mode(1); c.stats_reset()
+            c.render(cam, depth, chunk=chunk)
+            out[(path, chunk)] = (c.read_rgbf().view(np.uint32).copy(), c.read_argb().copy(), c.stats()["rays"], c.get_seeds())
+        finally:
+            c.close()
+    ref = out[(3, None)]
+    for key, got in out.items():
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2:] == ref[2:], key
+
+
 def _mixed_scene():
     """Everything the state machine has to get right at once: three lights (one near the scene, one behind most surfaces,
     one with zero power), nine spheres (an odd count: the pairwise sphere loop has a remainder), a vertical wall, a plane
