@@ -38,7 +38,12 @@ namespace
 #define RFX_BLOB_MINBLOCKS 8
 #endif
 
+#ifndef RFX_BLOB_TILE_W
+#define RFX_BLOB_TILE_W 4     // pixel tile of a warp: 4 x 8 (a multiple of 4: one 128-bit framebuffer store per 4 lanes)
+#endif
+
 constexpr int BLOB_THREADS = 128;
+constexpr uint32_t BLOB_TILE_W = RFX_BLOB_TILE_W, BLOB_TILE_H = 32 / RFX_BLOB_TILE_W;
 constexpr int BLOB_STACK = 24;          // entries per thread; the host only routes BVHs of depth <= BLOB_STACK - 2 here
 
 struct BlobView
@@ -498,8 +503,8 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
   __shared__ int stackMem[BLOB_STACK * BLOB_THREADS];
   const BlobView sc = blobView(sceneBlob);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t x = (blockIdx.x * (BLOB_THREADS / 32) + warp) * 4u + (lane & 3u);
-  const uint32_t y = y0 + blockIdx.y * 8u + (lane >> 2);
+  const uint32_t x = (blockIdx.x * (BLOB_THREADS / 32) + warp) * BLOB_TILE_W + (lane % BLOB_TILE_W);
+  const uint32_t y = y0 + blockIdx.y * BLOB_TILE_H + (lane / BLOB_TILE_W);
   const bool valid = x < fp.W && y < y1;
   uint32_t events = 0, packed = 0, qOut = 0;
   if (valid)
@@ -559,9 +564,9 @@ int launchTraceBlobFast(const TraceWork & w, int bvhDepth, cudaStream_t st)
   if (fp.p0 % fp.W != 0 || fp.p1 % fp.W != 0 || (uint64_t)fp.W * fp.H >= (1ull << 32)) return 0;
   if (bvhDepth > BLOB_STACK - 2) return 0;
   const uint64_t rows = (fp.p1 - fp.p0) / fp.W;
-  if (rows == 0 || (rows + 7) / 8 > 65535u) return 0;
-  const uint32_t tilesX = (fp.W + 3u) / 4u, warps = BLOB_THREADS / 32;
-  const dim3 grid((tilesX + warps - 1) / warps, (uint32_t)((rows + 7) / 8));
+  if (rows == 0 || (rows + BLOB_TILE_H - 1) / BLOB_TILE_H > 65535u) return 0;
+  const uint32_t tilesX = (fp.W + BLOB_TILE_W - 1) / BLOB_TILE_W, warps = BLOB_THREADS / 32;
+  const dim3 grid((tilesX + warps - 1) / warps, (uint32_t)((rows + BLOB_TILE_H - 1) / BLOB_TILE_H));
   k_trace_blob<<<grid, BLOB_THREADS, 0, st>>>(reinterpret_cast<const unsigned char *>(w.sceneBlob), fp, w.sampleStates, w.argbOut, w.counters,
                                              (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W), w.image);
   return 1;

@@ -172,11 +172,12 @@ def test_bvh_equals_brute_force(capi, oracle, n_side, size, depth):
 
 
 @pytest.mark.parametrize("which,size,depth,bvh", [("grid6", (128, 72), 8, 1), ("grid12", (161, 90), 6, 0), ("grid12", (160, 91), 6, 2),
-                                                   ("mixed", (250, 131), 12, 0), ("mixed", (64, 40), 12, 1)])
+                                                   ("mixed", (250, 131), 12, 0), ("mixed", (64, 40), 12, 1), ("grid2", (64, 40), 6, 1)])
 def test_blob_batch_kernel_equals_general_blob_kernel(capi, oracle, which, size, depth, bvh):
     """rfx_trace_blob.cu (state machine, shared-memory traversal stack; row-aligned one-sample ARGB slices of blob scenes) against
     k_trace: identical frames, ray counts and stream position, with and without the hierarchy, widths that are not a multiple of
-    the tile width, heights that are not a multiple of the tile height; and both meet the parity bar against the oracle."""
+    the tile width, heights that are not a multiple of the tile height, a hierarchy whose root is a leaf (4 spheres); and both meet the
+    parity bar against the oracle."""
     W, H = size
     scene = _mixed_scene() if which == "mixed" else S.synthetic_scene(int(which[4:]), floor=S.synthetic_texture(64, 64, 3), skybox=S.synthetic_texture(128, 96, 5))
     cams = [S.default_camera(), S.orbit_cameras(7)[3]]
