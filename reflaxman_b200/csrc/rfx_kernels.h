@@ -77,7 +77,7 @@ struct TraceWork
   TileOrder order;              // fast constant-bank kernel only
 };
 int launchTrace(const TraceWork & w, cudaStream_t st);                              // any scene: blob in global memory, BVH over the spheres
-// blob scenes, batch path (row-aligned slice, one sample per pixel, no jitter, ARGB and/or float image out): rfx_trace_blob.cu.  Returns 0 without launching when
+// blob scenes, row-aligned slices (one sample per pixel, grid SSAA, additive jitter; ARGB and/or float image out): rfx_trace_blob.cu.  Returns 0 without launching when
 // the work does not qualify (the caller uses launchTrace); bvhDepth = depth of the hierarchy the blob points at (0: none)
 int launchTraceBlobFast(const TraceWork & w, int bvhDepth, cudaStream_t st);
 // small scenes: constant-bank resident; *fastGrid (optional) receives the CTA count of the fast kernel's grid, 0 when the

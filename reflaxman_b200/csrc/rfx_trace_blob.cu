@@ -1,6 +1,6 @@
 // rfx_trace_blob.cu — K2 for scenes that do not fit the constant bank (config 4: 1024 spheres), batch path: a row-aligned
-// slice, one sample per pixel, ARGB and/or float image out.  Everything else about such scenes (SSAA, jitter, block preview,
-// ragged slices, signatures) stays
+// slice (ARGB and/or float image out; one sample per pixel for the batch path, grid SSAA and additive jitter for the Render API).
+// Everything else about such scenes (block preview, ragged slices, signatures) stays
 // on k_trace (rfx_kernels.cu), whose results this kernel reproduces bit for bit.
 //
 // It is the structure of the constant-bank kernel (rfx_trace_small.cu) applied to the scene blob in global memory:
@@ -495,6 +495,10 @@ __device__ __forceinline__ V3 traceBlob(const BlobView & sc, int * __restrict__ 
   return pix;
 }
 
+// K2 for row-aligned slices of blob scenes.  MULTI = false: one sample per pixel, no jitter (the batch path of the bench).
+// MULTI = true: the same tiling for grid SSAA (Render.cpp:174-196: the thread walks its s*s samples in the reference's ssx, ssy
+// order so the sum is formed in the same order) and additive jitter / accumulation (Render.cpp:177-178, :196-207).
+template <bool MULTI>
 __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob(const unsigned char * __restrict__ sceneBlob, const __grid_constant__ FrameParams fp,
                                                                 const uint32_t * __restrict__ sampleStates, uint32_t * __restrict__ argbOut,
                                                                 unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1,
@@ -506,45 +510,84 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
   const uint32_t x = (blockIdx.x * (BLOB_THREADS / 32) + warp) * BLOB_TILE_W + (lane % BLOB_TILE_W);
   const uint32_t y = y0 + blockIdx.y * BLOB_TILE_H + (lane / BLOB_TILE_W);
   const bool valid = x < fp.W && y < y1;
-  uint32_t events = 0, packed = 0, qOut = 0;
+  uint32_t nBounces = 0, nShadow = 0, packed = 0, qOut = 0;
   if (valid)
   {
     const uint32_t q = y * fp.W + x;
-    uint32_t s = __ldg(sampleStates + (q - y0 * fp.W));
     const float rx = float(x) - fp.wHalf;                                // Render.cpp:154-155
     const float ry = float(y) - fp.hHalf;
-    const V3 ray = mk((rx * fp.view[0] + ry * fp.view[1]) + fp.rz * fp.view[2],
-                      (rx * fp.view[3] + ry * fp.view[4]) + fp.rz * fp.view[5],
-                      (rx * fp.view[6] + ry * fp.view[7]) + fp.rz * fp.view[8]);
-    V3 rd;
-    rngTriple(s, rd.x, rd.y, rd.z);
-    const V3 c = traceBlob(sc, stackMem + threadIdx.x, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, events);
+    const V3 eye = mk(fp.eye[0], fp.eye[1], fp.eye[2]);
+    V3 c;
+    if (!MULTI)
+    {
+      uint32_t s = __ldg(sampleStates + (q - y0 * fp.W));
+      const V3 ray = mk((rx * fp.view[0] + ry * fp.view[1]) + fp.rz * fp.view[2],
+                        (rx * fp.view[3] + ry * fp.view[4]) + fp.rz * fp.view[5],
+                        (rx * fp.view[6] + ry * fp.view[7]) + fp.rz * fp.view[8]);
+      V3 rd;
+      rngTriple(s, rd.x, rd.y, rd.z);
+      uint32_t events = 0;
+      c = traceBlob(sc, stackMem + threadIdx.x, eye, ray, fp.reflNum, rd, events);   // one sample: colour / 1 == colour
+      nBounces = events & 0xFFFFu; nShadow = events >> 16;
+    }
+    else
+    {
+      const int sn = fp.sampleNum;
+      const uint32_t rel = q - y0 * fp.W;                                // pixel index inside the slice
+      float rndx = 0, rndy = 0;
+      if (fp.jitter)
+      {
+        uint32_t s = lcgJump(fp.seedRender, 2u * rel);                   // two draws per pixel, Render.cpp:177-178
+        s = 214013u * s + 2531011u; rndx = divExact(float((int)((s >> 16) & 0x7FFFu)), 32767.0f, RFX_RCP_32767);
+        s = 214013u * s + 2531011u; rndy = divExact(float((int)((s >> 16) & 0x7FFFu)), 32767.0f, RFX_RCP_32767);
+      }
+      c = mk(0.0f, 0.0f, 0.0f);
+      const uint32_t * st = sampleStates + (size_t)rel * (size_t)(sn * sn);
+#pragma unroll 1
+      for (int k = 0; k < sn * sn; k++)
+      {
+        const int ssx = k / sn, ssy = k - ssx * sn;
+        uint32_t s = __ldg(st + k);
+        V3 rd;
+        rngTriple(s, rd.x, rd.y, rd.z);
+        const float px = (rx + float(ssx) / float(sn)) + rndx;           // Render.cpp:184
+        const float py = (ry + float(ssy) / float(sn)) + rndy;
+        const V3 ray = mk((px * fp.view[0] + py * fp.view[1]) + fp.rz * fp.view[2],
+                          (px * fp.view[3] + py * fp.view[4]) + fp.rz * fp.view[5],
+                          (px * fp.view[6] + py * fp.view[7]) + fp.rz * fp.view[8]);
+        uint32_t events = 0;
+        const V3 one = traceBlob(sc, stackMem + threadIdx.x, eye, ray, fp.reflNum, rd, events);
+        nBounces += events & 0xFFFFu; nShadow += events >> 16;
+        c = vadd(c, one);
+      }
+      const float sq = float(sn * sn);
+      if (fabsf(sq) > RFX_VSN) c = mk(c.x / sq, c.y / sq, c.z / sq);     // Color::operator/=, Color.cpp:50-61
+    }
     packed = packArgb(c.x, c.y, c.z);
     qOut = q;
-    if (image)                                                           // Render.cpp:196-207, one sample: colour / 1 == colour
+    if (image)                                                           // Render.cpp:196-207
     {
       float * px = image + (size_t)q * 3;
       if (fp.accumulate) { px[0] = px[0] + c.x; px[1] = px[1] + c.y; px[2] = px[2] + c.z; }
       else { px[0] = c.x; px[1] = c.y; px[2] = c.z; }
     }
   }
-  if (!argbOut) goto count;
+  if (argbOut)
   {
-  // framebuffer: one 128-bit store per tile row (see k_trace_small)
-  const uint32_t p1 = __shfl_down_sync(0xffffffffu, packed, 1), p2 = __shfl_down_sync(0xffffffffu, packed, 2), p3 = __shfl_down_sync(0xffffffffu, packed, 3);
-  const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
-  if ((fp.W & 3u) == 0u && ((validMask >> (lane & ~3u)) & 0xFu) == 0xFu)
-  {
-    if ((lane & 3u) == 0u) *reinterpret_cast<uint4 *>(argbOut + qOut) = make_uint4(packed, p1, p2, p3);
-  }
-  else if (valid) argbOut[qOut] = packed;
+    // framebuffer: one 128-bit store per tile row (see k_trace_small)
+    const uint32_t p1 = __shfl_down_sync(0xffffffffu, packed, 1), p2 = __shfl_down_sync(0xffffffffu, packed, 2), p3 = __shfl_down_sync(0xffffffffu, packed, 3);
+    const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
+    if ((fp.W & 3u) == 0u && ((validMask >> (lane & ~3u)) & 0xFu) == 0xFu)
+    {
+      if ((lane & 3u) == 0u) *reinterpret_cast<uint4 *>(argbOut + qOut) = make_uint4(packed, p1, p2, p3);
+    }
+    else if (valid) argbOut[qOut] = packed;
   }
 
-count:
   if (counters)
   {
-    const uint32_t wb = __reduce_add_sync(0xffffffffu, events & 0xFFFFu);
-    const uint32_t ws = __reduce_add_sync(0xffffffffu, events >> 16);
+    const uint32_t wb = __reduce_add_sync(0xffffffffu, nBounces);
+    const uint32_t ws = __reduce_add_sync(0xffffffffu, nShadow);
     if (lane == 0)
     {
       const uint32_t slot = ((blockIdx.y * gridDim.x + blockIdx.x) * (BLOB_THREADS / 32) + warp) & 31u;
@@ -560,15 +603,17 @@ count:
 int launchTraceBlobFast(const TraceWork & w, int bvhDepth, cudaStream_t st)
 {
   const FrameParams & fp = w.fp;
-  if (fp.sampleNum != 1 || fp.jitter || w.sigOut || (!w.argbOut && !w.image) || fp.W == 0 || fp.stripWorld) return 0;
+  if (fp.sampleNum < 1 || fp.sampleNum > 64 || w.sigOut || (!w.argbOut && !w.image) || fp.W == 0 || fp.stripWorld) return 0;
   if (fp.p0 % fp.W != 0 || fp.p1 % fp.W != 0 || (uint64_t)fp.W * fp.H >= (1ull << 32)) return 0;
   if (bvhDepth > BLOB_STACK - 2) return 0;
   const uint64_t rows = (fp.p1 - fp.p0) / fp.W;
   if (rows == 0 || (rows + BLOB_TILE_H - 1) / BLOB_TILE_H > 65535u) return 0;
   const uint32_t tilesX = (fp.W + BLOB_TILE_W - 1) / BLOB_TILE_W, warps = BLOB_THREADS / 32;
   const dim3 grid((tilesX + warps - 1) / warps, (uint32_t)((rows + BLOB_TILE_H - 1) / BLOB_TILE_H));
-  k_trace_blob<<<grid, BLOB_THREADS, 0, st>>>(reinterpret_cast<const unsigned char *>(w.sceneBlob), fp, w.sampleStates, w.argbOut, w.counters,
-                                             (uint32_t)(fp.p0 / fp.W), (uint32_t)(fp.p1 / fp.W), w.image);
+  const unsigned char * blob = reinterpret_cast<const unsigned char *>(w.sceneBlob);
+  const uint32_t y0 = (uint32_t)(fp.p0 / fp.W), y1 = (uint32_t)(fp.p1 / fp.W);
+  if (fp.sampleNum == 1 && !fp.jitter) k_trace_blob<false><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.image);
+  else k_trace_blob<true><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.image);
   return 1;
 }
 
