@@ -224,6 +224,41 @@ def test_blob_batch_kernel_float_image_equals_general_blob_kernel(capi):
         assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2:] == ref[2:], key
 
 
+def _edge_case(case):
+    if case == "empty":          # nothing to hit, nothing to light: every ray goes to the skybox
+        scene = {"ambient": ((0.95, 0.95, 1.0), 0.15), "skybox": S.synthetic_texture(128, 96, 5), "textures": [], "lights": [], "objects": []}
+        return scene, 37, 5, 3, 1
+    scene = S.default_scene()
+    scene["lights"] = []         # ambient only: no shadow rays at all
+    return (scene, 1, 1, 20, 1) if case == "nolight_1x1" else (scene, 1, 67, 20, 2)
+
+
+@pytest.mark.parametrize("case", ["empty", "nolight_1x1", "nolight_1x67_ss2"])
+def test_edge_cases_match_oracle(capi, oracle, case):
+    """Empty scene, no lights, a single pixel, an image one pixel wide with 2x2 SSAA (tiles hang over three edges): every kernel
+    (constant-bank general and fast, blob batch, blob general) against the oracle, with identical ray counts and stream position."""
+    scene, W, H, depth, samples = _edge_case(case)
+    cam = S.default_camera()
+    o = oracle.OracleRender(scene, W, H, seed=7).render(cam, depth, samples)
+    _, oargb = o.resolve()
+    for path in (1, 2, 3):
+        c = capi.Context(0)
+        try:
+            c.load_scene(scene); c.set_seeds(7, 7); c.set_image_size(W, H)
+            c.force_path(path); c.stats_reset()
+            c.render(cam, depth, samples)
+            argb = c.read_argb()
+            st = c.stats()
+            assert st["rays"] == o.counters["rays"] and st["bounces"] == o.counters["bounces"], (case, path)
+            assert c.get_seeds()[0] == int(o.seeds[0]), (case, path)
+            cases.assert_parity(argb, oargb, "%s, kernel %d" % (case, path))
+            c.set_seeds(7, 7)
+            batch = c.render_frames([cam], depth, samples)[0]      # ARGB-only batch path (fast kernels)
+            assert np.array_equal(batch, argb), (case, path)
+        finally:
+            c.close()
+
+
 def _mixed_scene():
     """Everything the state machine has to get right at once: three lights (one near the scene, one behind most surfaces,
     one with zero power), nine spheres (an odd count: the pairwise sphere loop has a remainder), a vertical wall, a plane
