@@ -228,14 +228,27 @@ def _edge_case(case):
     if case == "empty":          # nothing to hit, nothing to light: every ray goes to the skybox
         scene = {"ambient": ((0.95, 0.95, 1.0), 0.15), "skybox": S.synthetic_texture(128, 96, 5), "textures": [], "lights": [], "objects": []}
         return scene, 37, 5, 3, 1
+    if case in ("constbank_full", "constbank_plus_one"):
+        # every array of the constant-bank scene at its capacity (16 spheres, 8 triangles, 2 planes, 4 lights) / one sphere more
+        # (the scene no longer fits and goes to the blob kernels, list walk)
+        scene = _mixed_scene()
+        for k in range(7 if case == "constbank_full" else 8):
+            scene["objects"].append(("sphere", (-4.0 + 1.1 * k, 0.35, -4.5 + 0.3 * k), 0.35, S.MT_METAL if k % 2 else S.MT_DIELECTRIC,
+                                     (0.4 + 0.07 * k, 0.9 - 0.05 * k, 0.6), 0.1 * k, 0.0))
+        for k in range(5):
+            scene["objects"].append(("tri", (-5.0 + 2.0 * k, 0.0, 4.0, -5.0 + 2.0 * k, 1.5, 4.0, -4.0 + 2.0 * k, 0.0, 4.0), S.MT_DIELECTRIC,
+                                     (0.9, 0.8 - 0.1 * k, 0.3), 0.5, 0.0, -1, (0.0, 0.0, 0.0, 1.0, 1.0, 0.0)))
+        scene["objects"].append(("plane", (0.0, 12.0, 0.0), (0.0, -1.0, 0.0), S.MT_METAL, (0.5, 0.5, 0.6), 0.2, 0.0))
+        return scene, 96, 54, 10, 1
     scene = S.default_scene()
     scene["lights"] = []         # ambient only: no shadow rays at all
     return (scene, 1, 1, 20, 1) if case == "nolight_1x1" else (scene, 1, 67, 20, 2)
 
 
-@pytest.mark.parametrize("case", ["empty", "nolight_1x1", "nolight_1x67_ss2"])
+@pytest.mark.parametrize("case", ["empty", "nolight_1x1", "nolight_1x67_ss2", "constbank_full", "constbank_plus_one"])
 def test_edge_cases_match_oracle(capi, oracle, case):
-    """Empty scene, no lights, a single pixel, an image one pixel wide with 2x2 SSAA (tiles hang over three edges): every kernel
+    """Empty scene, no lights, a single pixel, an image one pixel wide with 2x2 SSAA (tiles hang over three edges), the constant-bank scene at
+    capacity and one sphere past it: every kernel
     (constant-bank general and fast, blob batch, blob general) against the oracle, with identical ray counts and stream position."""
     scene, W, H, depth, samples = _edge_case(case)
     cam = S.default_camera()
