@@ -323,9 +323,11 @@ class Context:
         self._ck(self.L.rfx_enable_profiling(self.h, 1 if on else 0), "rfx_enable_profiling")
 
     def force_path(self, path):
+        """0 automatic, 1 constant-bank kernels when the scene fits, 2 blob kernels, 3 general blob kernel only (tests)."""
         self._ck(self.L.rfx_force_path(self.h, path), "rfx_force_path")
 
     def set_bvh_mode(self, mode):
+        """0 automatic (hierarchy over the spheres when there are more than 32), 1 always, 2 never (list walk)."""
         self._ck(self.L.rfx_set_bvh_mode(self.h, mode), "rfx_set_bvh_mode")
 
     def set_tile_ordering(self, on=True):
