@@ -52,6 +52,9 @@ typedef struct rfx_stats
   uint64_t d2h_bytes;       /* device->host bytes copied by the library */
   uint64_t trace_kernels;   /* K2 launches timed while profiling was enabled */
   double trace_kernel_ms;   /* their summed device time (CUDA events on the launching stream); 0 unless rfx_enable_profiling */
+  /* K2 launches by kernel family: constant-bank fast kernel (k_trace_small<FEAT, MULTI>), constant-bank general kernel
+   * (k_trace_small_any), blob batch kernel (k_trace_blob<MULTI>), blob general kernel (k_trace) */
+  uint64_t launches_small_fast, launches_small_any, launches_blob_fast, launches_blob_any;
 } rfx_stats;
 
 typedef struct rfx_device_info
@@ -156,6 +159,11 @@ RFX_API int rfx_synchronize(rfx_ctx * ctx);
 RFX_API int rfx_get_stats(rfx_ctx * ctx, rfx_stats * out);     /* synchronises */
 RFX_API int rfx_stats_reset(rfx_ctx * ctx);
 RFX_API int rfx_enable_profiling(rfx_ctx * ctx, int on);
+/* tuning / test hook; results never depend on an option.  "max_calls_per_launch": Scene::trace calls one random-stream pass and
+ * one trace launch may cover (default 2^25 = 128 MB of ranked states; large SSAA factors and 8K frames are rendered in chunks of
+ * this many calls — tests lower it to drive the chunk loop at small sizes).  "copy_streams": device->host streams
+ * rfx_render_frames alternates between (1 or 2, default 1). */
+RFX_API int rfx_set_option(rfx_ctx * ctx, const char * name, int64_t value);
 /* kernel selection: 0 = automatic (constant-bank kernel when the scene fits, the general blob kernel otherwise),
  * 1 = constant-bank kernel if it fits, 2 = always the blob kernels (batch kernel for row-aligned one-sample ARGB slices, the
  * general one otherwise), 3 = always the general blob kernel.  Results are identical; tests use it. */

@@ -72,6 +72,7 @@ def lib(path=None):
     L.rfxo_get_env.argtypes = [C.c_void_p, _fp, _fp]
     L.rfxo_trace_one.argtypes = [C.c_void_p, _fp, _fp, C.c_int, _fp, _fp, _u32p]
     L.rfxo_rand_dirs.argtypes = [_u32p, C.c_uint64, _fp]
+    L.rfxo_plane_probe.argtypes = [_fp, C.c_int, _fp]
     L.rfxo_render_pass.restype = C.c_int
     L.rfxo_render_pass.argtypes = [C.c_void_p, _fp, _fp, C.c_float, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int,
                                    C.c_int, _fp, _u32p, C.POINTER(Counters), _u32p, C.c_int]
@@ -193,6 +194,26 @@ def rand_dirs(seed, n):
     out = np.zeros((n, 3), np.float32)
     lib().rfxo_rand_dirs(s.ctypes.data_as(_u32p), n, out.ctypes.data_as(_fp))
     return out, int(s[0])
+
+
+def plane_probe(inputs):
+    """Plane::trace restatement on [n, 12] float32 inputs (pos, norm, origin, ray) -> [n, 12] outputs (see rfxo_plane_probe)."""
+    a = np.ascontiguousarray(inputs, dtype=np.float32).reshape(-1, 12)
+    out = np.zeros((a.shape[0], 12), np.float32)
+    lib().rfxo_plane_probe(a.ctypes.data_as(_fp), a.shape[0], out.ctypes.data_as(_fp))
+    return out
+
+
+def run_plane_probe(n, seed):
+    """The reference's own Plane::trace on n seeded inputs (oracle/_ref/ref_plane_probe) -> ([n, 12] inputs, [n, 12] outputs)."""
+    exe = os.path.join(REF_DIR, "ref_plane_probe")
+    if not os.access(exe, os.X_OK):
+        raise FileNotFoundError(exe)
+    with tempfile.TemporaryDirectory() as td:
+        outp = os.path.join(td, "planes.bin")
+        subprocess.run([exe, str(n), str(seed), outp], check=True)
+        raw = np.fromfile(outp, dtype=np.float32).reshape(n, 24)
+    return raw[:, :12].copy(), raw[:, 12:].copy()
 
 
 def camera_lookat(eye, at):

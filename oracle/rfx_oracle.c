@@ -669,6 +669,38 @@ void rfxo_trace_one(const rfxo_scene * s, const float origin[3], const float ray
   if (sig) *sig = h;
 }
 
+/* Plane::trace (Plane.cpp:36-73) on n independent (pos, norm, origin, ray) inputs of 12 floats each, for the pin against the
+ * reference's own Plane::trace (oracle/ref_plane_probe.cpp).  out: 12 floats per input = hit, drop[3], norm[3], reflected[3],
+ * distance, shadowHit (the NULL-output call of Scene.cpp:135); outputs of a miss stay 0 as in the probe. */
+void rfxo_plane_probe(const float * in, int n, float * out)
+{
+  rfxo_counters k;
+  memset(&k, 0, sizeof(k));
+  for (int i = 0; i < n; i++)
+  {
+    const float * p = in + 12 * i;
+    float * o = out + 12 * i;
+    Obj pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.kind = OBJ_PLANE;
+    pl.pos = v3(p[0], p[1], p[2]);
+    pl.norm = v3(p[3], p[4], p[5]);
+    Hit h;
+    memset(&h, 0, sizeof(h));
+    memset(o, 0, 12 * sizeof(float));
+    const int hit = plane_trace(NULL, &pl, v3(p[6], p[7], p[8]), v3(p[9], p[10], p[11]), &h, &k);
+    o[0] = (float)hit;
+    if (hit)
+    {
+      o[1] = h.drop.x; o[2] = h.drop.y; o[3] = h.drop.z;
+      o[4] = h.norm.x; o[5] = h.norm.y; o[6] = h.norm.z;
+      o[7] = h.reflect.x; o[8] = h.reflect.y; o[9] = h.reflect.z;
+      o[10] = h.dist;
+    }
+    o[11] = (float)plane_trace(NULL, &pl, v3(p[6], p[7], p[8]), v3(p[9], p[10], p[11]), NULL, &k);
+  }
+}
+
 /* n successive Vector3::randomInsideSphere(1.0f) draws starting from *seed; seed is advanced */
 void rfxo_rand_dirs(uint32_t * seed, uint64_t n, float * out_xyz)
 {

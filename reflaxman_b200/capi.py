@@ -20,7 +20,8 @@ _u32p = C.POINTER(C.c_uint32)
 
 class RfxStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays", "bounces", "shadow_rays", "samples", "kernel_launches",
-                                          "h2d_bytes", "d2h_bytes", "trace_kernels")] + [("trace_kernel_ms", C.c_double)]
+                                          "h2d_bytes", "d2h_bytes", "trace_kernels")] + [("trace_kernel_ms", C.c_double)] + \
+               [(n, C.c_uint64) for n in ("launches_small_fast", "launches_small_any", "launches_blob_fast", "launches_blob_any")]
 
     def as_dict(self):
         return {n: (float if n == "trace_kernel_ms" else int)(getattr(self, n)) for n, _ in self._fields_}
@@ -78,6 +79,7 @@ SYMBOLS = [
     ("rfx_get_stats", C.c_int, [C.c_void_p, C.POINTER(RfxStats)]),
     ("rfx_stats_reset", C.c_int, [C.c_void_p]),
     ("rfx_enable_profiling", C.c_int, [C.c_void_p, C.c_int]),
+    ("rfx_set_option", C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     ("rfx_force_path", C.c_int, [C.c_void_p, C.c_int]),
     ("rfx_set_bvh_mode", C.c_int, [C.c_void_p, C.c_int]),
     ("rfx_set_tile_ordering", C.c_int, [C.c_void_p, C.c_int]),
@@ -321,6 +323,10 @@ class Context:
 
     def enable_profiling(self, on=True):
         self._ck(self.L.rfx_enable_profiling(self.h, 1 if on else 0), "rfx_enable_profiling")
+
+    def set_option(self, name, value):
+        """tuning / test hook (include/reflax_c.h): "max_calls_per_launch", "copy_streams"; results never depend on it"""
+        self._ck(self.L.rfx_set_option(self.h, name.encode(), int(value)), "rfx_set_option")
 
     def force_path(self, path):
         """0 automatic, 1 constant-bank kernels when the scene fits, 2 blob kernels, 3 general blob kernel only (tests)."""

@@ -32,6 +32,7 @@ struct HostObj
   Material mat;             // order = insertion index
   float center[3], sqRadius, radius;
   Triangle tri;
+  float triVerts[9];        // the three vertices as given (bounds of the drop points for the BVH margins)
   Plane plane;
 };
 
@@ -71,9 +72,9 @@ template <typename T> inline size_t align16(T v) { return ((size_t)v + 15) & ~(s
 // Median split on the widest centroid axis, leaves of <= 4 spheres, boxes inflated by `margin`.  The hierarchy only
 // selects which spheres receive the exact reference test on the device; it never decides a hit.
 struct BvhNode { float lo[3], hi[3]; int a, b; };
-struct BvhPrim { float c[3], r; int index; };
+struct BvhPrim { float c[3], r, m; int index; };   // m: this sphere's box margin (see uploadScene)
 
-int buildBvhRec(std::vector<BvhNode> & nodes, std::vector<BvhPrim> & prims, int begin, int end, float margin, int depth, int & maxDepth)
+int buildBvhRec(std::vector<BvhNode> & nodes, std::vector<BvhPrim> & prims, int begin, int end, int depth, int & maxDepth)
 {
   const int me = (int)nodes.size();
   nodes.push_back(BvhNode());
@@ -82,8 +83,8 @@ int buildBvhRec(std::vector<BvhNode> & nodes, std::vector<BvhPrim> & prims, int 
   for (int i = begin; i < end; i++)
     for (int k = 0; k < 3; k++)
     {
-      lo[k] = std::min(lo[k], prims[i].c[k] - prims[i].r - margin);
-      hi[k] = std::max(hi[k], prims[i].c[k] + prims[i].r + margin);
+      lo[k] = std::min(lo[k], prims[i].c[k] - prims[i].r - prims[i].m);
+      hi[k] = std::max(hi[k], prims[i].c[k] + prims[i].r + prims[i].m);
       clo[k] = std::min(clo[k], prims[i].c[k]);
       chi[k] = std::max(chi[k], prims[i].c[k]);
     }
@@ -101,8 +102,8 @@ int buildBvhRec(std::vector<BvhNode> & nodes, std::vector<BvhPrim> & prims, int 
   const int mid = (begin + end) / 2;
   std::nth_element(prims.begin() + begin, prims.begin() + mid, prims.begin() + end,
                    [axis](const BvhPrim & x, const BvhPrim & y) { return x.c[axis] < y.c[axis] || (x.c[axis] == y.c[axis] && x.index < y.index); });
-  n.a = buildBvhRec(nodes, prims, begin, mid, margin, depth + 1, maxDepth);
-  n.b = buildBvhRec(nodes, prims, mid, end, margin, depth + 1, maxDepth);
+  n.a = buildBvhRec(nodes, prims, begin, mid, depth + 1, maxDepth);
+  n.b = buildBvhRec(nodes, prims, mid, end, depth + 1, maxDepth);
   nodes[me] = n;
   return me;
 }
@@ -112,7 +113,8 @@ int buildBvhRec(std::vector<BvhNode> & nodes, std::vector<BvhPrim> & prims, int 
 struct rfx_ctx
 {
   int device = 0;
-  cudaStream_t stream = nullptr, copyStream = nullptr, lastStream = nullptr;
+  cudaStream_t stream = nullptr, copyStream[2] = { nullptr, nullptr }, lastStream = nullptr;
+  int copyStreams = 1;                      // D2H streams rfx_render_frames alternates between (rfx_set_option "copy_streams")
   cudaDeviceProp prop;
   mutable std::string err;
 
@@ -160,9 +162,13 @@ struct rfx_ctx
   int * dStatus = nullptr;
   float * dRays = nullptr; size_t raysCap = 0;   // rfx_trace_rays scratch
 
-  // ---- staging for the host batch path
-  uint32_t * dFrame[3] = { nullptr, nullptr, nullptr }; size_t frameCap = 0;
-  cudaEvent_t evRendered[3] = { nullptr, nullptr, nullptr }, evCopied[3] = { nullptr, nullptr, nullptr };
+  // ---- staging for the host batch path (all slots share one capacity; they are always reallocated together)
+  static const int FRAME_SLOTS = 4;
+  uint32_t * dFrame[FRAME_SLOTS] = { nullptr, nullptr, nullptr, nullptr }; size_t frameCap = 0;
+  uint32_t * dResolve = nullptr; size_t resolveCap = 0;   // K3 output of the Render-API read path (its own buffer and capacity)
+  uint64_t maxCallsPerLaunch = 1ull << 25;    // bounds the ranked-state scratch (128 MB) for huge SSAA factors / 8K frames
+  float bvhReach[6] = { 0, 0, 0, 0, 0, 0 };   // box of ray origins the hierarchy's margins were sized for (lo xyz, hi xyz)
+  cudaEvent_t evRendered[FRAME_SLOTS] = { nullptr, nullptr, nullptr, nullptr }, evCopied[FRAME_SLOTS] = { nullptr, nullptr, nullptr, nullptr };
 
   // ---- counters
   unsigned long long * dCounters = nullptr;   // [32][2]
@@ -276,20 +282,50 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
   if (wantBvh)
   {
     std::vector<BvhPrim> prims(sph.size());
-    float extent = 1.0f;
+    // Box margins.  The hierarchy must never cull a sphere the reference's exact test (Sphere.cpp:49-57) would report, and that
+    // test is noisy: with v = origin - centre, disc = b*b - 4a*c carries an absolute rounding error of at most ~40 * 2^-24 * a|v|^2
+    // (three-term dot products, the square, the product), while a ray that misses the sphere by m has disc = 4a(r^2 - m^2).  A
+    // "noise hit" therefore needs m^2 - r^2 < 6e-7 |v|^2, i.e. m - r < min(3e-7 |v|^2 / r, 7.7e-4 |v|).  |v| is bounded by the
+    // diagonal R of the box that holds every possible ray origin — the camera eye and all drop points (on spheres and
+    // triangles) — and every centre; each sphere's box is inflated by twice its own bound.  (Planes are unbounded: a drop point
+    // on a plane can lie outside the box; the reference's Scene cannot hold planes, and rfx_set_camera re-flattens the scene
+    // when the eye leaves the box.)
+    float lo[3] = { ctx->eye[0], ctx->eye[1], ctx->eye[2] }, hi[3] = { ctx->eye[0], ctx->eye[1], ctx->eye[2] };
+    for (size_t i = 0; i < sph.size(); i++)
+      for (int k = 0; k < 3; k++)
+      {
+        lo[k] = std::min(lo[k], sph[i]->center[k] - sph[i]->radius);
+        hi[k] = std::max(hi[k], sph[i]->center[k] + sph[i]->radius);
+      }
+    for (const HostObj * t : tri)
+    {
+      for (int v = 0; v < 3; v++)
+        for (int k = 0; k < 3; k++)
+        {
+          lo[k] = std::min(lo[k], t->triVerts[3 * v + k]);
+          hi[k] = std::max(hi[k], t->triVerts[3 * v + k]);
+        }
+    }
+    for (int k = 0; k < 3; k++)   // room for the camera to move before the margins have to be recomputed
+    {
+      const float pad = 0.1f * (hi[k] - lo[k]);
+      lo[k] -= pad; hi[k] += pad;
+    }
+    const double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2];
+    const double R = sqrt(dx * dx + dy * dy + dz * dz);
+    for (int k = 0; k < 3; k++) { ctx->bvhReach[k] = lo[k]; ctx->bvhReach[3 + k] = hi[k]; }
     for (size_t i = 0; i < sph.size(); i++)
     {
       BvhPrim & p = prims[i];
       memcpy(p.c, sph[i]->center, sizeof(p.c));
       p.r = sph[i]->radius;
       p.index = (int)i;
-      for (int k = 0; k < 3; k++) extent = std::max(extent, fabsf(p.c[k]) + p.r);
+      const double noise = std::min(3e-7 * R * R / std::max((double)p.r, 1e-30), 7.7e-4 * R);
+      p.m = (float)(2.0 * noise + 1e-6 * R);
     }
-    // the exact sphere test is wrong by ~1e-6 of the scene extent at most; the boxes get three orders of magnitude more
-    const float margin = 1e-3f * extent;
     std::vector<BvhNode> nodes;
     int maxDepth = 0;
-    buildBvhRec(nodes, prims, 0, (int)prims.size(), margin, 0, maxDepth);
+    buildBvhRec(nodes, prims, 0, (int)prims.size(), 0, maxDepth);
     if (maxDepth < 30)   // traversal stack is 32 deep; a median split of < 2^30 spheres never gets here
     {
       // leaves are padded to 4 slots: bvhPrims[4 * leaf + k] = sphere index (k < count), and — for the batch kernel, which tests a
@@ -462,8 +498,6 @@ int rankSamples(rfx_ctx * ctx, uint64_t n, bool skipOnly, cudaStream_t st, uint6
   return RFX_OK;
 }
 
-const uint64_t MAX_CALLS_PER_LAUNCH = 1ull << 25;   // bounds the ranked-state scratch (128 MB) for huge SSAA factors / 8K frames
-
 // Fills w.order for a fast-kernel launch and remembers what the launch will have recorded (see TileOrder).  History is
 // only reused by a launch over exactly the same grid; any other launch of the fast kernel starts a new history.
 int armTileOrder(rfx_ctx * ctx, TraceWork & w, cudaStream_t st)
@@ -506,7 +540,7 @@ int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, boo
     if (sn > 0)
     {
       const uint64_t per = (uint64_t)sn * sn;
-      uint64_t pix = MAX_CALLS_PER_LAUNCH / per;
+      uint64_t pix = ctx->maxCallsPerLaunch / per;
       if (pix < 1) pix = 1;
       if (cur % ctx->W == 0 && pix >= ctx->W) pix -= pix % ctx->W;   // whole rows keep the chunk on the tiled fast kernel
       end = preStates ? p1 : std::min(p1, cur + pix);
@@ -543,9 +577,15 @@ int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, boo
       }
       const bool useSmall = ctx->forcePath >= 2 ? false : ctx->smallOk;
       if (useSmall && (rc = armTileOrder(ctx, w, st)) != RFX_OK) return rc;
-      if (useSmall) ctx->stats.kernel_launches += launchTraceSmall(ctx->small, w, st);
-      else if (ctx->forcePath != 3 && launchTraceBlobFast(w, ctx->bvhDepth, st)) ctx->stats.kernel_launches += 1;
-      else ctx->stats.kernel_launches += launchTrace(w, st);
+      if (useSmall)
+      {
+        uint32_t fastGrid = 0;
+        const int nl = launchTraceSmall(ctx->small, w, st, &fastGrid);
+        ctx->stats.kernel_launches += nl;
+        (fastGrid ? ctx->stats.launches_small_fast : ctx->stats.launches_small_any) += nl;
+      }
+      else if (ctx->forcePath != 3 && launchTraceBlobFast(w, ctx->bvhDepth, st)) { ctx->stats.kernel_launches += 1; ctx->stats.launches_blob_fast += 1; }
+      else { const int nl = launchTrace(w, st); ctx->stats.kernel_launches += nl; ctx->stats.launches_blob_any += nl; }
       if (evB) CK(cudaEventRecord(evB, st));
       CK(cudaGetLastError());
       ctx->stats.samples += nCalls;
@@ -596,7 +636,7 @@ int rfx_create(rfx_ctx ** out, int device)
   cudaError_t err = cudaSuccess;
   auto step = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
   step(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  step(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) step(cudaStreamCreateWithFlags(&ctx->copyStream[i], cudaStreamNonBlocking));
   if (initRngTables() != 0) step(cudaErrorUnknown);
   step(cudaMalloc((void **)&ctx->dRng, 2 * sizeof(uint32_t)));
   step(cudaMalloc((void **)&ctx->dRngPrefix, 3 * (size_t)(RNG_CLASS_BLOCKS + 1) * sizeof(uint32_t)));
@@ -612,7 +652,7 @@ int rfx_create(rfx_ctx ** out, int device)
   step(cudaMalloc((void **)&ctx->dStatus, sizeof(int)));
   step(cudaMalloc((void **)&ctx->dCounters, 64 * sizeof(unsigned long long)));
   step(cudaMalloc((void **)&ctx->dLut, 256 * sizeof(float)));
-  for (int i = 0; i < 3; i++)
+  for (int i = 0; i < rfx_ctx::FRAME_SLOTS; i++)
   {
     step(cudaEventCreateWithFlags(&ctx->evRendered[i], cudaEventDisableTiming));
     step(cudaEventCreateWithFlags(&ctx->evCopied[i], cudaEventDisableTiming));
@@ -647,14 +687,15 @@ void rfx_destroy(rfx_ctx * ctx)
   cudaFree(ctx->dRngPrefix); cudaFree(ctx->dRngLocate); cudaFree(ctx->dSampleStates); cudaFree(ctx->dStatus);
   cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dBvhNodes); cudaFree(ctx->dBvhPrims); cudaFree(ctx->dTileLists[0]); cudaFree(ctx->dTileLists[1]); cudaFree(ctx->dTileCounts);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
-  for (int i = 0; i < 3; i++)
+  cudaFree(ctx->dResolve);
+  for (int i = 0; i < rfx_ctx::FRAME_SLOTS; i++)
   {
     cudaFree(ctx->dFrame[i]);
     if (ctx->evRendered[i]) cudaEventDestroy(ctx->evRendered[i]);
     if (ctx->evCopied[i]) cudaEventDestroy(ctx->evCopied[i]);
   }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
-  if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+  for (int i = 0; i < 2; i++) if (ctx->copyStream[i]) cudaStreamDestroy(ctx->copyStream[i]);
   delete ctx;
 }
 
@@ -737,6 +778,7 @@ int rfx_add_triangle(rfx_ctx * ctx, const float v[9], int mtype, const float rgb
   invertColumns(hsub(v2, v0), hsub(v1, v0), nn, o.tri.ax);      // Triangle.cpp:19-20
   o.tri.v0[0] = v0.x; o.tri.v0[1] = v0.y; o.tri.v0[2] = v0.z;
   o.tri.n[0] = n.x; o.tri.n[1] = n.y; o.tri.n[2] = n.z;
+  memcpy(o.triVerts, v, sizeof(o.triVerts));
   ctx->objs.push_back(o);
   ctx->sceneDirty = true;
   return (int)ctx->objs.size() - 1;
@@ -803,6 +845,10 @@ int rfx_set_camera(rfx_ctx * ctx, const float eye[3], const float view[9], float
   memcpy(ctx->eye, eye, sizeof(float) * 3);
   memcpy(ctx->view, view, sizeof(float) * 9);
   ctx->fov = fov;
+  // the BVH's box margins were sized for ray origins inside bvhReach (uploadScene): an eye outside it re-flattens the scene
+  if (ctx->bvhDepth > 0)
+    for (int k = 0; k < 3; k++)
+      if (!(eye[k] >= ctx->bvhReach[k] && eye[k] <= ctx->bvhReach[3 + k])) ctx->sceneDirty = true;
   return RFX_OK;
 }
 
@@ -996,7 +1042,10 @@ int rfx_render_strips(rfx_ctx * ctx, uint32_t strip_rows, uint32_t world, uint32
     CK(cudaEventRecord(evA, st));
   }
   if ((rc = armTileOrder(ctx, w, st)) != RFX_OK) return rc;
-  ctx->stats.kernel_launches += launchTraceSmall(ctx->small, w, st);
+  {
+    const int nl = launchTraceSmall(ctx->small, w, st);
+    ctx->stats.kernel_launches += nl; ctx->stats.launches_small_fast += nl;
+  }
   if (evB) CK(cudaEventRecord(evB, st));
   CK(cudaGetLastError());
   ctx->stats.samples += calls / world;
@@ -1098,10 +1147,10 @@ static int readResolved(rfx_ctx * ctx, float * rgbf, uint32_t * argb, int divide
   const size_t n = (size_t)ctx->W * ctx->H;
   if (argb)
   {
-    if ((rc = ensure(ctx, ctx->dFrame[0], ctx->frameCap, n)) != RFX_OK) return rc;
-    ctx->stats.kernel_launches += launchResolve(ctx->dImage, n, counter, nullptr, ctx->dFrame[0], ctx->stream);
+    if ((rc = ensure(ctx, ctx->dResolve, ctx->resolveCap, n)) != RFX_OK) return rc;
+    ctx->stats.kernel_launches += launchResolve(ctx->dImage, n, counter, nullptr, ctx->dResolve, ctx->stream);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(argb, ctx->dFrame[0], n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(argb, ctx->dResolve, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.d2h_bytes += n * 4;
   }
   if (rgbf)
@@ -1228,11 +1277,11 @@ int rfx_render_frames_device(rfx_ctx * ctx, int n_frames, const float * cams, in
   if (reflect_num <= 0 || sample_num == 0) return fail(ctx, RFX_ERR_ARG, "rfx_render_frames_device: reflect_num must be > 0 and sample_num != 0");
   ctx->sampleNum = sample_num;
   const uint64_t perFrame = callsIn(ctx, 0, total);
-  const int group = (int)std::max<uint64_t>(1, MAX_CALLS_PER_LAUNCH / std::max<uint64_t>(perFrame, 1));
+  const int group = (int)std::max<uint64_t>(1, ctx->maxCallsPerLaunch / std::max<uint64_t>(perFrame, 1));
   for (int f0 = 0; f0 < n_frames; f0 += group)
   {
     const int g = std::min(group, n_frames - f0);
-    const bool pre = perFrame <= MAX_CALLS_PER_LAUNCH;
+    const bool pre = perFrame <= ctx->maxCallsPerLaunch;
     if (pre && (rc = rankSamples(ctx, perFrame * g, false, st)) != RFX_OK) return rc;
     for (int f = f0; f < f0 + g; f++)
     {
@@ -1256,41 +1305,40 @@ int rfx_render_frames(rfx_ctx * ctx, int n_frames, const float * cams, int refle
   if ((rc = useStream(ctx, st)) != RFX_OK) return rc;
   if ((rc = uploadScene(ctx, st)) != RFX_OK) return rc;
   const uint64_t total = (uint64_t)ctx->W * ctx->H;
-  // three device frame slots: render frame f into slot f%3 on the compute stream while the copy stream drains older slots
-  for (int i = 0; i < 3; i++)
+  // FRAME_SLOTS device frame slots: render frame f into slot f % FRAME_SLOTS on the compute stream while the copy stream(s)
+  // drain older slots into the caller's host buffer
+  const int NS = rfx_ctx::FRAME_SLOTS;
+  if (ctx->frameCap < total || !ctx->dFrame[0])
   {
-    size_t cap = ctx->dFrame[i] ? ctx->frameCap : 0;
-    if (cap < total)
-    {
-      CK(cudaDeviceSynchronize());
-      for (int j = 0; j < 3; j++) { if (ctx->dFrame[j]) cudaFree(ctx->dFrame[j]); ctx->dFrame[j] = nullptr; }
-      for (int j = 0; j < 3; j++) CK(cudaMalloc((void **)&ctx->dFrame[j], total * 4));
-      ctx->frameCap = total;
-      break;
-    }
+    CK(cudaDeviceSynchronize());
+    for (int j = 0; j < NS; j++) { if (ctx->dFrame[j]) cudaFree(ctx->dFrame[j]); ctx->dFrame[j] = nullptr; }
+    ctx->frameCap = 0;
+    for (int j = 0; j < NS; j++) CK(cudaMalloc((void **)&ctx->dFrame[j], total * 4));
+    ctx->frameCap = total;
   }
   if (reflect_num <= 0 || sample_num == 0) return fail(ctx, RFX_ERR_ARG, "rfx_render_frames: reflect_num must be > 0 and sample_num != 0");
   ctx->sampleNum = sample_num;
   const uint64_t perFrame = callsIn(ctx, 0, total);
-  const int group = (int)std::max<uint64_t>(1, MAX_CALLS_PER_LAUNCH / std::max<uint64_t>(perFrame, 1));
-  const bool pre = perFrame <= MAX_CALLS_PER_LAUNCH;
+  const int group = (int)std::max<uint64_t>(1, ctx->maxCallsPerLaunch / std::max<uint64_t>(perFrame, 1));
+  const bool pre = perFrame <= ctx->maxCallsPerLaunch;
   for (int f = 0; f < n_frames; f++)
   {
-    const int slot = f % 3;
+    const int slot = f % NS;
+    cudaStream_t cs = ctx->copyStream[ctx->copyStreams > 1 ? (f & 1) : 0];
     if (pre && f % group == 0 && (rc = rankSamples(ctx, perFrame * std::min(group, n_frames - f), false, st)) != RFX_OK) return rc;
-    if (f >= 3) CK(cudaStreamWaitEvent(st, ctx->evCopied[slot], 0));   // slot free again?
+    if (f >= NS) CK(cudaStreamWaitEvent(st, ctx->evCopied[slot], 0));   // slot free again?
     if ((rc = beginFrame(ctx, cams + 13 * (size_t)f, reflect_num, sample_num)) != RFX_OK) return rc;
     if ((rc = renderRange(ctx, 0, total, ctx->dFrame[slot], false, st,
                           pre ? ctx->dSampleStates + (size_t)(f % group) * perFrame : nullptr)) != RFX_OK) return rc;
     ctx->cursor = total;
     ctx->inProgress = false;
     CK(cudaEventRecord(ctx->evRendered[slot], st));
-    CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evRendered[slot], 0));
-    CK(cudaMemcpyAsync(argb_host + (size_t)f * total, ctx->dFrame[slot], total * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
-    CK(cudaEventRecord(ctx->evCopied[slot], ctx->copyStream));
+    CK(cudaStreamWaitEvent(cs, ctx->evRendered[slot], 0));
+    CK(cudaMemcpyAsync(argb_host + (size_t)f * total, ctx->dFrame[slot], total * 4, cudaMemcpyDeviceToHost, cs));
+    CK(cudaEventRecord(ctx->evCopied[slot], cs));
     ctx->stats.d2h_bytes += total * 4;
   }
-  CK(cudaStreamSynchronize(ctx->copyStream));
+  for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(ctx->copyStream[i]));
   CK(cudaStreamSynchronize(st));
   return checkStatus(ctx);
 }
@@ -1361,6 +1409,24 @@ int rfx_set_bvh_mode(rfx_ctx * ctx, int mode)
   ctx->bvhMode = mode;
   ctx->sceneDirty = true;
   return RFX_OK;
+}
+
+int rfx_set_option(rfx_ctx * ctx, const char * name, int64_t value)
+{
+  if (!ctx || !name) return RFX_ERR_ARG;
+  if (!strcmp(name, "max_calls_per_launch"))
+  {
+    if (value < 1) return fail(ctx, RFX_ERR_ARG, "rfx_set_option: max_calls_per_launch must be >= 1");
+    ctx->maxCallsPerLaunch = (uint64_t)value;
+    return RFX_OK;
+  }
+  if (!strcmp(name, "copy_streams"))
+  {
+    if (value < 1 || value > 2) return fail(ctx, RFX_ERR_ARG, "rfx_set_option: copy_streams must be 1 or 2");
+    ctx->copyStreams = (int)value;
+    return RFX_OK;
+  }
+  return fail(ctx, RFX_ERR_ARG, std::string("rfx_set_option: unknown option ") + name);
 }
 
 int rfx_enable_profiling(rfx_ctx * ctx, int on)

@@ -103,9 +103,9 @@ __device__ __forceinline__ float cubeLikePowf(float x)
 // powf(x, y) of Scene.cpp:175 (specular lobe: x in (2^-63, 1], y >= 1).  glibc's powf is correctly rounded in all but a
 // vanishing fraction of cases, so the target is RN_float(x^y).  Evaluated in binary64 as 2^(y*log2 x) with ~2^-50 relative
 // error, rounded once to float: wrong only when x^y lies within 2^-26 relative of a float rounding boundary, about one
-// call in 10^7 (tools/pow_check.cu measures it against CUDA's correctly-rounded-to-double pow()).  It replaces CUDA's
+// call in 10^7 (tools/pow_check.cu measures it against CUDA's pow(double, double), < 1 ulp of binary64, rounded to float).  It replaces CUDA's
 // pow(double, double), whose 1500 instructions of special-case and extended-precision code evicted the kernel's working
-// set from the 32 KB instruction cache.  Requires 0 < x < inf; any finite y.
+// set from the 32 KB instruction cache.  Requires 0 < x < inf; y finite or +-inf (a NaN exponent is not propagated).
 static __device__ __noinline__ float powLikePowf(float xf, float yf)
 {
   const double x = (double)xf;                      // exact; float denormals are normal doubles
@@ -137,9 +137,10 @@ static __device__ __noinline__ float powLikePowf(float xf, float yf)
   p = fma(p, s2, 1.0 / 5.0);
   p = fma(p, s2, 1.0 / 3.0);
   const double lnm = fma(s * s2, p, s) * 2.0;       // 2s + 2s^3 p
-  // log2 x = e + ln m * log2(e), log2(e) split into a 32-bit head and a tail so that the head product is exact enough
+  // log2 x = e + ln m * log2(e): one fma (the product is not rounded before e is added)
   const double L = fma(lnm, 1.4426950408889634074, (double)e);
-  double z = (double)yf * L;
+  // x == 1 gives L == 0 exactly and powf(1, y) is 1 for every y, also y = +inf (0 * inf would be NaN)
+  double z = (L == 0.0) ? 0.0 : (double)yf * L;
   if (!(z > -1000.0)) z = -1000.0;                  // x^y underflows binary32 long before (also absorbs -inf)
   if (!(z < 1000.0)) z = 1000.0;
   const double n = rint(z);

@@ -851,12 +851,8 @@ int launchTrace(const TraceWork & w, cudaStream_t st)
   }
   if (nThreads == 0) return 0;
   const uint32_t smem = RFX_BIG_SMEM_SCENE ? ((w.sceneBytes + 15u) & ~15u) : 0u;
-  static uint32_t smemOptedIn = 0;
-  if (smem > 48 * 1024 && smem > smemOptedIn)
-  {
-    cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smemOptedIn = smem;
-  }
+  // the opt-in is per device and cheap: set it on every such launch (a process may drive several GPUs)
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
   const uint32_t blocks = (uint32_t)((nThreads + TRACE_THREADS - 1) / TRACE_THREADS);
   k_trace<<<blocks, TRACE_THREADS, smem, st>>>(reinterpret_cast<const unsigned char *>(w.sceneBlob), smem, fp, w.sampleStates,
                                                w.image, w.argbOut, w.sigOut, w.counters, tiled);
@@ -904,12 +900,9 @@ int launchTraceRays(const void * sceneBlob, uint32_t sceneBytes, int n, const fl
 {
   if (n <= 0) return 0;
   const uint32_t smem = (sceneBytes + 15u) & ~15u;
-  static uint32_t optedIn = 0;
-  if (smem > 48 * 1024 && smem > optedIn)
-  {
-    cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    optedIn = smem;
-  }
+  // the opt-in is per device and cheap: set it on every such launch (a process may drive several GPUs); a failure is
+  // left as the sticky error the caller's cudaGetLastError() reports
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
   k_trace_rays<<<(n + TRACE_THREADS - 1) / TRACE_THREADS, TRACE_THREADS, smem, st>>>(reinterpret_cast<const unsigned char *>(sceneBlob), smem, n,
                                                                                       origins, rays, reflNum, sampleStates, rgbOut, counters);
   return 1;

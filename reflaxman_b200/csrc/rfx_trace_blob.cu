@@ -860,6 +860,7 @@ int launchTraceBlobFast(const TraceWork & w, int bvhDepth, cudaStream_t st)
   if (fp.sampleNum < 1 || fp.sampleNum > 64 || w.sigOut || (!w.argbOut && !w.image) || fp.W == 0 || fp.stripWorld) return 0;
   if (fp.p0 % fp.W != 0 || fp.p1 % fp.W != 0 || (uint64_t)fp.W * fp.H >= (1ull << 32)) return 0;
   if (bvhDepth > BLOB_STACK - 2) return 0;
+  if (w.argbOut && (fp.W & 3u) == 0u && (reinterpret_cast<uintptr_t>(w.argbOut) & 15u) != 0u) return 0;   // 128-bit stores need a 16-byte aligned frame
   const uint64_t rows = (fp.p1 - fp.p0) / fp.W;
   if (rows == 0 || (rows + BLOB_TILE_H - 1) / BLOB_TILE_H > 65535u) return 0;
   const uint32_t tilesX = (fp.W + BLOB_TILE_W - 1) / BLOB_TILE_W, warps = BLOB_THREADS / 32;

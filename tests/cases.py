@@ -17,10 +17,16 @@ def small_synth():
     return S.synthetic_scene(n_side=6, floor=S.synthetic_texture(128, 128, 3))
 
 
+def config4_scene():
+    """BASELINE.json configs[3]: 1024 spheres on a jittered 32x32 grid, textured floor and sky (the bench's scene)"""
+    return S.synthetic_scene(32, floor=S.synthetic_texture(1024, 1024, 11), skybox=S.synthetic_texture(2048, 1536, 7))
+
+
 SCENES = {
     "default": S.default_scene,
     "textured": textured_default,
     "synth36": small_synth,
+    "synth1024": config4_scene,
 }
 
 GOLDEN = [
@@ -32,6 +38,7 @@ GOLDEN = [
     "default_64x48_2frames",
     "textured_160x120_d20",
     "synth36_128x72_d8",
+    "synth1024_480x270_d8",
 ]
 
 

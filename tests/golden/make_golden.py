@@ -28,6 +28,10 @@ def small_synth():
     return S.synthetic_scene(n_side=6, floor=S.synthetic_texture(128, 128, 3))
 
 
+def config4_scene():
+    return S.synthetic_scene(32, floor=S.synthetic_texture(1024, 1024, 11), skybox=S.synthetic_texture(2048, 1536, 7))
+
+
 CASES = [
     # name, scene factory (None = the reference's own built-in scene), W, H, refl, samples, additive passes, frames, seed, keep float
     ("default_160x120_d20", None, 160, 120, 20, 1, 0, 1, 12345, True),
@@ -38,14 +42,24 @@ CASES = [
     ("default_64x48_2frames", None, 64, 48, 20, 1, 0, 2, 12345, True),
     ("textured_160x120_d20", textured_default, 160, 120, 20, 1, 0, 1, 12345, True),
     ("synth36_128x72_d8", small_synth, 128, 72, 8, 1, 0, 1, 12345, True),
+    # BASELINE.json configs[3] (1024 spheres + textured floor and sky) at a size the reference's list walk finishes in ~15 s
+    ("synth1024_480x270_d8", config4_scene, 480, 270, 8, 1, 0, 1, 12345, False),
 ]
 
 
-def main():
+def main(only=None):
+    """only: names of the cases to (re)generate (default: everything, ~3 minutes)"""
     O.build(ref=True)
     assert O.have_ref(), "oracle/_ref/ref_render missing: /root/reference not available?"
     index = {}
+    if not only or "plane_probe" in only:
+        # Plane::trace is unreachable through Scene: the reference's own function probed directly (oracle/ref_plane_probe.cpp)
+        inputs, outputs = O.run_plane_probe(4096, 777)
+        np.savez_compressed(os.path.join(OUT, "plane_probe.npz"), inputs=inputs, outputs=outputs)
+        print("plane_probe", hashlib.sha256(outputs.tobytes()).hexdigest()[:16], "hits %.3f" % outputs[:, 0].mean())
     for name, factory, W, H, refl, samples, add, frames, seed, keepf in CASES:
+        if only and name not in only:
+            continue
         scene = factory() if factory else None
         info, imgs = O.run_reference(W, H, refl=refl, samples=samples, additive_passes=add, frames=frames, scene=scene, seed=seed)
         data = {"W": W, "H": H, "refl": refl, "samples": samples, "additive": add, "frames": frames, "seed": seed}
@@ -57,8 +71,11 @@ def main():
         index[name] = hashlib.sha256(imgs[-1][1].tobytes()).hexdigest()
         print(name, index[name][:16])
     # full-size hashes only (images are too big to commit): config 1 and config 2
+    # configs 1, 2 and 3 (7680x4320, a reference screenshot preset, Pulse.cpp:20)
+    if only and "full_size" not in only:
+        return
     with open(os.path.join(OUT, "full_size_sha256.txt"), "w") as f:
-        for W, H in ((1024, 768), (1920, 1080)):
+        for W, H in ((1024, 768), (1920, 1080), (7680, 4320)):
             info, imgs = O.run_reference(W, H, refl=20, seed=12345)
             hs = hashlib.sha256(imgs[0][1].tobytes()).hexdigest()
             hf = hashlib.sha256(imgs[0][0].tobytes()).hexdigest()
@@ -67,4 +84,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])

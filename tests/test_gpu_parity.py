@@ -32,7 +32,8 @@ def test_gpu_matches_golden(capi, name, path):
         for i, (rgbf, argb) in enumerate(frames):
             st = cases.assert_parity(argb, g["argb%d" % i], "%s frame %d" % (name, i))
             # float image: identical up to powf rounding (<= a few ulp of a colour contribution)
-            assert np.max(np.abs(rgbf - g["rgbf%d" % i])) < 2e-5, name
+            if "rgbf%d" % i in g:
+                assert np.max(np.abs(rgbf - g["rgbf%d" % i])) < 2e-5, name
             assert st["frac_exact"] > 0.995, (name, st)
     finally:
         eng.close()
