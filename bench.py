@@ -32,9 +32,42 @@ sys.path.insert(0, ROOT)
 
 W, H, DEPTH = 1920, 1080, 20
 CENSUS_FLOP_PER_PIXEL = 1301.7          # SURVEY.md §8(d), config 2 (our own census build counts 1270.9)
-NCU_DRAM_BYTES_PER_LAUNCH = 8396800     # dram__bytes_read.sum + dram__bytes_write.sum of k_trace_small, profiles/r1_final (ncu --set full)
+NCU_RAW_CSV = ("profiles/r2_final/prof_k_trace_small_raw.csv", "profiles/r1_final/prof_k_trace_small_raw.csv")   # ncu --set full, newest first
+UNFUSED_SCALAR_CEILING_TFLOPS = 35.8    # measured: scalar FMUL+FADD issue ceiling (profiles/microbench_r1.jsonl); a balanced FMUL2+FADD2 mix measures 73.1
 RAYS_PER_FRAME_CANONICAL = 7493076      # oracle counters, config 2, seed 12345 (3.6136 rays/pixel); recomputed live when possible
 METRIC = "Mrays/s at 1920x1080, default scene, reflection depth 20 (frames/s alongside)"
+WORKLOAD = "config2: default scene 1920x1080, reflection depth 20, 1 sample/pixel, default camera; a step is frames_per_step successive frames (randDir stream continues)"
+L2_NOTE = ("GPU arm: outputs larger than L2 (frames_per_step x 8.3 MB of ARGB written per step per GPU against the 126 MB L2), inputs are a <1 KB scene; "
+           "CPU arm: not applicable")
+
+
+def shared_config(frames):
+    """the same `config` object in both arms' lines (the driver compares them)"""
+    return {"workload": WORKLOAD, "width": W, "height": H, "depth": DEPTH, "frames_per_step": frames, "l2": L2_NOTE}
+
+
+def ncu_dram_bytes_per_launch():
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of one k_trace_small launch, read from the committed
+    `ncu --set full` raw page (profiles/), per launch; None when no capture is in the tree"""
+    import csv
+    for rel in NCU_RAW_CSV:
+        path = os.path.join(ROOT, rel)
+        if not os.path.exists(path):
+            continue
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        for vals in rows[2:]:
+            kernel = vals[hdr.index("Kernel Name")]
+            if "k_trace_small" not in kernel:
+                continue
+            total = 0.0
+            for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(name)
+                v = float(vals[i].replace(",", ""))
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+                total += v * scale
+            return int(total), rel
+    return None, None
 
 
 def parse():
@@ -46,6 +79,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
     ap.add_argument("--workload", default="config2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs 3 / 4 / 5 measurements of the `secondary` object")
     return ap.parse_args()
 
 
@@ -160,23 +194,24 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/%s was not built (needs /root/reference at build time)" % binary}))
         return
     rays = canonical_rays_per_frame()
+    F = args.frames
     times = []
     for i in range(args.warmup + args.steps):
-        t, _ = reference_cpu_run(binary, cores, frames=1)   # bounded sample: one config-2 frame per step
+        t, _ = reference_cpu_run(binary, cores, frames=F)   # one step: the same F successive config-2 frames as the GPU arm's step
         if i >= args.warmup:
             times.append(t)
     total = sum(times)
-    fps = len(times) / total
+    fps = len(times) * F / total
     val = fps * rays / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "frames_per_s": fps,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2: default scene 1920x1080 depth 20, 1 frame per step", "width": W, "height": H, "depth": DEPTH,
-                   "frames_per_step": 1},
+        "config": shared_config(F),
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "reference",
-                         "sample": "1 frame per step; unmodified reference sources, reference flags -Ofast -fexpensive-optimizations (+NDEBUG), "
-                                   "harness-parallel: %d processes x interleaved rows through Scene::trace (the reference itself is single-threaded)" % cores},
+                         "sample": "%d frames per step; unmodified reference sources, reference flags -Ofast -fexpensive-optimizations (+NDEBUG), "
+                                   "harness-parallel: %d processes x interleaved rows through Scene::trace (the reference itself is single-threaded); "
+                                   "rays per frame = canonical config-2 count (%d)" % (F, cores, rays)},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -204,7 +239,10 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ctx = capi.Context(local)
+    t_create = time.perf_counter()
+    ctx = capi.Context(local)                 # rfx_create: builds the 8.4 MB accept-count table of the LCG cycle (k_rng_table)
+    ctx.synchronize()
+    create_ms = 1e3 * (time.perf_counter() - t_create)
     scene = S.default_scene()
     ctx.load_scene(scene)
     ctx.set_image_size(W, H)
@@ -214,7 +252,7 @@ def run_ours(args):
     info = ctx.device_info()
 
     # frame sharding: rank r owns frames [r * per_rank, (r+1) * per_rank) of the global sequence; skip the randDir stream there
-    steps_total = 2 * (Wm + K) + 2
+    steps_total = 2 * (Wm + K) + 3
     per_rank = steps_total * F
     if rank > 0:
         ctx.skip_samples(rank * per_rank * W * H)
@@ -275,6 +313,17 @@ def run_ours(args):
     ctx.enable_profiling(False)
     k2_ms_per_frame = stp["trace_kernel_ms"] / max(stp["trace_kernels"], 1)
     k2_share = stp["trace_kernel_ms"] / (ms / K)
+    # the same with the tile-order history dropped before every frame: what the FIRST frame over a grid costs (index order),
+    # and what an interactive front end whose renderNext slices never repeat pays on every launch
+    ctx.enable_profiling(True)
+    ctx.stats_reset()
+    for f in range(min(F, 8)):
+        ctx.set_tile_ordering(True)           # resets the history
+        ctx.render_frames_device(cams[f:f + 1], DEPTH, 1, out_dev.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    stc = ctx.stats()
+    ctx.enable_profiling(False)
+    k2_cold_ms = stc["trace_kernel_ms"] / max(stc["trace_kernels"], 1)
 
     # ---------------- end-to-end arm through the C ABI with host buffers
     def e2e_step():
@@ -292,6 +341,21 @@ def run_ours(args):
     e2e_s = maxreduce(time.perf_counter() - t0)
     sampler.end()
     clocks = sampler.stop() if rank == 0 else None
+    # copy-only ceiling of the same box, same buffers: F frames of 8.3 MB device -> pinned host per step on every rank at once, no
+    # rendering.  e2e cannot exceed it; at 4-8 GPUs it is what binds (the host side of the box absorbs ~95 GB/s in total).
+    def copy_step():
+        for f in range(F):
+            out_host[f].copy_(out_dev[f], non_blocking=True)
+    for _ in range(2):
+        copy_step()
+    barrier()
+    t0 = time.perf_counter()
+    KC = max(3, K // 2)
+    for _ in range(KC):
+        copy_step()
+    torch.cuda.synchronize()
+    copy_s = maxreduce(time.perf_counter() - t0)
+    d2h_ceiling_fps = KC * F * world / copy_s
     if world > 1:
         dist.barrier()
     st2 = ctx.stats()
@@ -300,12 +364,10 @@ def run_ours(args):
     h2d = st2["h2d_bytes"] / K + cams.nbytes
     d2h = st2["d2h_bytes"] / K
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---------------- roofline (FP32 CUDA cores; this path is neither HBM- nor tensor-bound, SURVEY §8d)
+    info = ctx.device_info()
+    ctx.close()
+    del out_dev
+    torch.cuda.set_stream(torch.cuda.default_stream())
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -313,17 +375,39 @@ def run_ours(args):
         pass
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     fp32_peak = 2 * 128 * info["sm_count"] * sm_max * 1e6 / 1e12          # FFMA peak, TFLOP/s (MEASURED_PEAKS.json has no FP32 entry)
+
+    # ---------------- BASELINE.json configs[2..4] (every rank takes part; device-timed, max over ranks)
+    secondary = None
+    if not args.no_secondary:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_extra
+        env = bench_extra.Env()
+        secondary = {"config3_split_8k_frame": bench_extra.config3(env, steps=10, warmup=3),
+                     "config5_orbit_240_frames": bench_extra.config5(env, steps=3, warmup=3)}
+        if world == 1:
+            secondary["config4_1024_spheres_depth_sweep"] = bench_extra.config4(env, steps=5, fp32_peak_tflops=fp32_peak)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline (FP32 CUDA cores; this path is neither HBM- nor tensor-bound, SURVEY §8d)
     flops_per_frame = CENSUS_FLOP_PER_PIXEL * W * H
     achieved = flops_per_frame / (k2_ms_per_frame * 1e-3) / 1e12
+    traffic, traffic_src = ncu_dram_bytes_per_launch()
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                "kernel": "k_trace_small", "kernel_ms_per_launch": k2_ms_per_frame, "kernel_share_of_step": k2_share,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "k_trace_small<0,false>", "kernel_ms_per_launch": k2_ms_per_frame, "kernel_share_of_step": k2_share,
+                "kernel_ms_per_launch_cold": k2_cold_ms,
                 "note": "bound is FP32 CUDA-core issue (neither hbm nor tensor: >= 80 flop per mandatory byte); traffic = dram__bytes_read+write of one "
-                        "launch from the ncu --set full capture in profiles/ (the 8.3 MB ARGB frame stays in the 126 MB L2 until evicted); "
-                        "achieved = SURVEY census 1301.7 flop/pixel x 1920x1080 per launch / mean k_trace_small duration (CUDA events on its stream); "
+                        "launch, read from the committed ncu --set full raw page (the 8.3 MB ARGB frame stays in the 126 MB L2 until evicted); "
+                        "achieved = SURVEY census 1301.7 flop/pixel x 1920x1080 per launch / mean k_trace_small duration (CUDA events on its stream, "
+                        "warm = tiles started in the cost order the previous frame recorded; cold = first frame over a grid, index order); "
                         "peak = 2*128*SMs*sm_max_mhz (FFMA; MEASURED_PEAKS.json has no FP32 entry; microbench measured 70.4). The arithmetic "
-                        "must stay un-fused for parity, so 0.5 is the ceiling: measured FMUL+FADD ceiling 35.8 TFLOP/s (profiles/microbench_r1.jsonl)",
-                "unfused_ceiling_tflops": 35.8, "frac_of_unfused_ceiling": achieved / 35.8}
+                        "must stay un-fused for parity: scalar FMUL+FADD issue tops out at 35.8 TFLOP/s, a balanced packed FMUL2+FADD2 mix at 73.1 "
+                        "(profiles/microbench_r1.jsonl)",
+                "unfused_scalar_ceiling_tflops": UNFUSED_SCALAR_CEILING_TFLOPS, "frac_of_unfused_scalar_ceiling": achieved / UNFUSED_SCALAR_CEILING_TFLOPS}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -345,16 +429,18 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "Mrays/s", "frames_per_s": fps,
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2: default scene 1920x1080, reflection depth 20, 1 sample/pixel, default camera; %d successive frames per GPU per step "
-                               "(randDir stream continues), frames sharded across GPUs without communication" % F,
-                   "width": W, "height": H, "depth": DEPTH, "frames_per_step_per_gpu": F,
-                   "l2": "outputs larger than L2: %d MB of ARGB written per step per GPU; inputs are a <1 KB scene" % (F * W * H * 4 // 2 ** 20),
-                   "rays_per_frame": rays_total / frames_total},
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "frames_per_s": frames_total / e2e_s, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "config": shared_config(F),
+        "frames_per_step_per_gpu": F, "rays_per_frame": rays_total / frames_total,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "frames_per_s": frames_total / e2e_s, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "d2h_copy_only_frames_per_s": d2h_ceiling_fps, "d2h_copy_only_GBps": d2h_ceiling_fps * W * H * 4 / 1e9,
+                "frac_of_d2h_ceiling": (frames_total / e2e_s) / d2h_ceiling_fps, "frac_of_device_resident": e2e_value / value,
+                "binds": "device->host copies (box ceiling)" if (frames_total / e2e_s) / d2h_ceiling_fps > 0.85 else "rendering"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "secondary": secondary,
+        "context_create_ms": create_ms,
         "device": info["name"],
     }
     print(json.dumps(line))
@@ -369,6 +455,6 @@ if __name__ == "__main__":
     elif a.workload in ("config3", "config4", "config5"):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_extra
-        getattr(bench_extra, a.workload)(a)
+        bench_extra.main(a)
     else:
         run_ours(a)
