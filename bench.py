@@ -243,6 +243,8 @@ def run_ours(args):
     ctx = capi.Context(local)                 # rfx_create: builds the 8.4 MB accept-count table of the LCG cycle (k_rng_table)
     ctx.synchronize()
     create_ms = 1e3 * (time.perf_counter() - t_create)
+    if os.environ.get("RFX_COPY_STREAMS"):    # A/B knob of the e2e pipeline (tools/r2_session2.sh); default 1
+        ctx.set_option("copy_streams", int(os.environ["RFX_COPY_STREAMS"]))
     scene = S.default_scene()
     ctx.load_scene(scene)
     ctx.set_image_size(W, H)

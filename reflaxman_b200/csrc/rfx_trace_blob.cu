@@ -38,9 +38,6 @@ namespace
 #ifndef RFX_BLOB_NEAR
 #define RFX_BLOB_NEAR 1      // pair nodes: nearer child first
 #endif
-#ifndef RFX_BLOB_COMPACT
-#define RFX_BLOB_COMPACT 0    // experiment: segment-synchronous CTA with path packing (see k_trace_blob_compact)
-#endif
 #ifndef RFX_BLOB_MINBLOCKS
 #define RFX_BLOB_MINBLOCKS 8
 #endif
@@ -604,253 +601,6 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
   }
 }
 
-#if RFX_BLOB_COMPACT
-// EXPERIMENT (not built by default, not measured yet — DESIGN.md §9): paths of one tile end at different segments, so 14 of 32 lanes
-// work on average.  Here the CTA advances all its paths one segment at a time (closest-hit query, its shadow queries, shading) and
-// between segments packs the surviving paths of its four tiles into the lowest threads through shared memory, so whole warps
-// retire instead of idling lane by lane.  Unlike lane-level regeneration the packed paths are all at the same segment and come
-// from a 16x8-pixel neighbourhood.  Which thread carries a path does not change any value it computes.
-
-// One segment of Scene::trace (one trip of the loop at Scene.cpp:80): returns true when the path is finished (pix is final)
-__device__ __forceinline__ bool segmentBlob(const BlobView & sc, int * __restrict__ stack, V3 & qo, V3 & qd, V3 randDir, V3 & mul, V3 & pix,
-                                            uint32_t & events, int reflNumber)
-{
-  const SceneHeader & h = *sc.h;
-  V3 o = qo, d = qd;
-  bool shadowQuery = false;
-  int li = 0, hidx = -1;
-  V3 norm = d, reflect = d, color = mul, sumLight = mk(0.0f, 0.0f, 0.0f), sumSpec = sumLight;
-  float normLen = 0.0f, reflectLen = 0.0f, mrefl = 0.0f;
-  float rfs = 0.0f;
-
-  for (;;)
-  {
-    Hit hit;
-    hit.dist = FLT_MAX; hit.idx = -1; hit.order = 0x7FFFFFFF; hit.t = 0; hit.u = 0; hit.v = 0;
-    intersectBlob(sc, stack, o, d, shadowQuery ? hidx : -1, shadowQuery, hit);
-
-    if (!shadowQuery)
-    {
-      events++;
-      if (hit.idx < 0)
-      {
-        float u, v;
-        skyDirToUv(d, vlen(d), h.halfTileW, h.halfTileH, u, v);
-        const V3 sky = texSampleRef(h.skyTex >= 0 ? &sc.tex[h.skyTex] : nullptr, h.byteLut, u, v);
-        pix = mk(clamp01(pix.x + (mul.x * sky.x) * h.env[0]), clamp01(pix.y + (mul.y * sky.y) * h.env[1]),
-                 clamp01(pix.z + (mul.z * sky.z) * h.env[2]));            // Scene.cpp:230-231
-        return true;
-      }
-      const V3 full = vscale(d, hit.t);
-      o = vadd(o, full);                                                   // drop point
-      const Material m = sc.mats[hit.idx];
-      color = mk(m.r, m.g, m.b);
-      mrefl = m.reflectivity;
-      const bool dielectric = m.type == 1;
-      hidx = hit.idx;
-      if (hit.idx < h.nSpheres)
-      {
-        const float4 s = __ldg(&sc.spheres[hit.idx]);
-        norm = mk(o.x - s.x, o.y - s.y, o.z - s.z);                        // Sphere.cpp:67
-      }
-      else if (hit.idx < h.nSpheres + h.nTris)
-      {
-        const Triangle & tr = sc.tris[hit.idx - h.nSpheres];
-        norm = mk(tr.n[0], tr.n[1], tr.n[2]);
-        if (m.tex >= 0)
-        {
-          const float tx = (hit.u * tr.tuv[0] + hit.v * tr.tuv[1]) + 0.0f;   // Triangle.cpp:91
-          const float ty = (hit.u * tr.tuv[2] + hit.v * tr.tuv[3]) + 0.0f;
-          color = texSampleRef(&sc.tex[m.tex], h.byteLut, tr.tu0 + tx, tr.tv0 + ty);
-        }
-      }
-      else
-      {
-        const Plane & pl = sc.planes[hit.idx - h.nSpheres - h.nTris];
-        norm = mk(pl.n[0], pl.n[1], pl.n[2]);
-      }
-      reflect = reflectVec(full, norm);
-      normLen = vlen(norm);
-      reflectLen = vlen(reflect);
-      rfs = -0.8f;                                                         // metal, Scene.cpp:207
-      if (dielectric)                                                      // Scene.cpp:192-196
-      {
-        const float a = vlen(d) * normLen;
-        const float cosA = (a > RFX_VSN) ? clamp01(((d.x * -norm.x + d.y * -norm.y) + d.z * -norm.z) / a) : 0.0f;
-        rfs = 0.2f + 0.8f * cubeLikePowf(1.0f - cosA);
-      }
-      li = 0;
-    }
-    else
-    {
-      const Light L = sc.lights[li];                                       // Scene.cpp:125-186
-      if (hit.idx < 0)
-      {
-        const V3 toLight = mk(L.ox - o.x, L.oy - o.y, L.oz - o.z);
-        const float facing = vdot(toLight, norm);
-        const float toLightLen = vlen(toLight);
-        float a = toLightLen * normLen;
-        const float lightDropCos = (a > RFX_VSN) ? facing / a : 0.0f;
-        if (L.power > RFX_VSN)
-        {
-          sumLight.x = sumLight.x + (L.r * lightDropCos) * L.power;       // Scene.cpp:156
-          sumLight.y = sumLight.y + (L.g * lightDropCos) * L.power;
-          sumLight.z = sumLight.z + (L.b * lightDropCos) * L.power;
-        }
-        a = vsqlen(toLight);
-        const float larsc = (a > RFX_VSN) ? 1.0f - L.radius * L.radius / a : 0.0f;   // Scene.cpp:160
-        if (larsc > 0)
-        {
-          const V3 nl = (toLightLen > RFX_VSN) ? mk(toLight.x / toLightLen, toLight.y / toLightLen, toLight.z / toLightLen) : toLight;
-          const V3 dtl = vadd(nl, vscale(randDir, 1.0f - mrefl));
-          a = vlen(dtl) * reflectLen;
-          float rsc = (a > RFX_VSN) ? vdot(dtl, reflect) / a : 0.0f;
-          rsc = clamp01(rsc + (1.0f - sqrtf(larsc)));
-          if (rsc > RFX_VSN && L.radius > RFX_VSN)
-          {
-            const float sp = powLikePowf(rsc, 1 + 3 * mrefl * toLightLen / L.radius) * mrefl;   // Scene.cpp:175
-            sumSpec.x = sumSpec.x + L.r * sp;
-            sumSpec.y = sumSpec.y + L.g * sp;
-            sumSpec.z = sumSpec.z + L.b * sp;
-          }
-        }
-      }
-      li++;
-    }
-
-    bool cast = false;                                                     // Scene.cpp:118-129
-    for (; li < h.nLights; li++)
-    {
-      const Light L = sc.lights[li];
-      const V3 toLight = mk(L.ox - o.x, L.oy - o.y, L.oz - o.z);
-      if (vdot(toLight, norm) > RFX_VSN)
-      {
-        d = vadd(toLight, vscale(randDir, L.radius));                      // Scene.cpp:129
-        cast = true;
-        break;
-      }
-    }
-    if (cast)
-    {
-      shadowQuery = true;
-      events += 0x10000u;
-      continue;
-    }
-
-    sumLight = mk(h.ambient[0] * h.ambientPower + sumLight.x, h.ambient[1] * h.ambientPower + sumLight.y,
-                  h.ambient[2] * h.ambientPower + sumLight.z);             // Scene.cpp:189
-    const bool dielectric = rfs > 0.0f;
-    const float rf = fabsf(rfs);
-    const float k = 1.0f - rf;
-    const V3 fin = mk(((color.x * k) * sumLight.x + sumSpec.x) * mul.x, ((color.y * k) * sumLight.y + sumSpec.y) * mul.y,
-                      ((color.z * k) * sumLight.z + sumSpec.z) * mul.z);   // Scene.cpp:198-199 / 209-210
-    if (dielectric) mul = vscale(mul, rf);                                 // Scene.cpp:202
-    else mul = mk(mul.x * (color.x * rf), mul.y * (color.y * rf), mul.z * (color.z * rf));   // Scene.cpp:213
-    pix = mk(clamp01(pix.x + fin.x), clamp01(pix.y + fin.y), clamp01(pix.z + fin.z));
-    if (mul.x < 0.01f && mul.y < 0.01f && mul.z < 0.01f) return true;
-    if ((int)(events & 0xFFFFu) >= reflNumber) return true;               // ++refl < reflNumber, Scene.cpp:80
-    const V3 rn = (reflectLen > RFX_VSN) ? mk(reflect.x / reflectLen, reflect.y / reflectLen, reflect.z / reflectLen) : reflect;
-    qo = o;
-    qd = vadd(rn, vscale(randDir, 1.0f - mrefl));                          // Scene.cpp:226
-    return false;
-  }
-}
-
-constexpr int PATH_WORDS = 17;   // qo, qd, randDir, mul, pix (3 each), pixel index, events
-
-__global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob_compact(const unsigned char * __restrict__ sceneBlob, const __grid_constant__ FrameParams fp,
-                                                                const uint32_t * __restrict__ sampleStates, uint32_t * __restrict__ argbOut,
-                                                                unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1)
-{
-  __shared__ int stackMem[BLOB_STACK * BLOB_THREADS];
-  __shared__ float xchg[PATH_WORDS][BLOB_THREADS];
-  __shared__ uint32_t warpAlive[2][BLOB_THREADS / 32];
-  const BlobView sc = blobView(sceneBlob);
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t x = (blockIdx.x * (BLOB_THREADS / 32) + warp) * BLOB_TILE_W + (lane % BLOB_TILE_W);
-  const uint32_t y = y0 + blockIdx.y * BLOB_TILE_H + (lane / BLOB_TILE_W);
-  bool alive = x < fp.W && y < y1;
-  V3 qo = mk(fp.eye[0], fp.eye[1], fp.eye[2]), qd = qo, rd = qo, mul = mk(1.0f, 1.0f, 1.0f), pix = mk(0.0f, 0.0f, 0.0f);
-  uint32_t q = 0, events = 0, totBounces = 0, totShadow = 0;
-  if (alive)
-  {
-    q = y * fp.W + x;
-    uint32_t s = __ldg(sampleStates + (q - y0 * fp.W));
-    const float rx = float(x) - fp.wHalf;                                // Render.cpp:154-155
-    const float ry = float(y) - fp.hHalf;
-    qd = mk((rx * fp.view[0] + ry * fp.view[1]) + fp.rz * fp.view[2],
-            (rx * fp.view[3] + ry * fp.view[4]) + fp.rz * fp.view[5],
-            (rx * fp.view[6] + ry * fp.view[7]) + fp.rz * fp.view[8]);
-    rngTriple(s, rd.x, rd.y, rd.z);
-    if (fp.reflNum <= 0) { argbOut[q] = packArgb(0.0f, 0.0f, 0.0f); alive = false; }
-  }
-
-  for (uint32_t round = 0;; round++)
-  {
-    if (alive && segmentBlob(sc, stackMem + threadIdx.x, qo, qd, rd, mul, pix, events, fp.reflNum))
-    {
-      argbOut[q] = packArgb(pix.x, pix.y, pix.z);
-      totBounces += events & 0xFFFFu;
-      totShadow += events >> 16;
-      alive = false;
-    }
-    // ---- pack the surviving paths of the CTA into its lowest threads
-    const uint32_t m = __ballot_sync(0xffffffffu, alive);
-    uint32_t * cnt = warpAlive[round & 1u];          // double-buffered: a fast warp's next write cannot overtake a slow warp's reads
-    if (lane == 0) cnt[warp] = __popc(m);
-    __syncthreads();
-    uint32_t total = 0, before = 0, warpsBusy = 0;
-#pragma unroll
-    for (uint32_t w = 0; w < BLOB_THREADS / 32; w++)
-    {
-      const uint32_t n = cnt[w];
-      if (w < warp) before += n;
-      total += n;
-      warpsBusy += n != 0u;
-    }
-    if (total == 0) break;                           // uniform over the CTA
-    if ((total + 31u) / 32u < warpsBusy)             // packing retires at least one warp (uniform over the CTA)
-    {
-      if (alive)
-      {
-        const uint32_t slot = before + __popc(m & ((1u << lane) - 1u));
-        xchg[0][slot] = qo.x; xchg[1][slot] = qo.y; xchg[2][slot] = qo.z;
-        xchg[3][slot] = qd.x; xchg[4][slot] = qd.y; xchg[5][slot] = qd.z;
-        xchg[6][slot] = rd.x; xchg[7][slot] = rd.y; xchg[8][slot] = rd.z;
-        xchg[9][slot] = mul.x; xchg[10][slot] = mul.y; xchg[11][slot] = mul.z;
-        xchg[12][slot] = pix.x; xchg[13][slot] = pix.y; xchg[14][slot] = pix.z;
-        xchg[15][slot] = __uint_as_float(q); xchg[16][slot] = __uint_as_float(events);
-      }
-      __syncthreads();
-      alive = threadIdx.x < total;
-      if (alive)
-      {
-        const uint32_t t = threadIdx.x;
-        qo = mk(xchg[0][t], xchg[1][t], xchg[2][t]);
-        qd = mk(xchg[3][t], xchg[4][t], xchg[5][t]);
-        rd = mk(xchg[6][t], xchg[7][t], xchg[8][t]);
-        mul = mk(xchg[9][t], xchg[10][t], xchg[11][t]);
-        pix = mk(xchg[12][t], xchg[13][t], xchg[14][t]);
-        q = __float_as_uint(xchg[15][t]); events = __float_as_uint(xchg[16][t]);
-      }
-      // the next stores into xchg come after the next round's __syncthreads, which every thread reaches after these loads
-    }
-  }
-
-  if (counters)
-  {
-    const uint32_t wb = __reduce_add_sync(0xffffffffu, totBounces);
-    const uint32_t ws = __reduce_add_sync(0xffffffffu, totShadow);
-    if (lane == 0)
-    {
-      const uint32_t slot = ((blockIdx.y * gridDim.x + blockIdx.x) * (BLOB_THREADS / 32) + warp) & 31u;
-      atomicAdd(&counters[slot * 2], (unsigned long long)wb);
-      atomicAdd(&counters[slot * 2 + 1], (unsigned long long)ws);
-    }
-  }
-}
-#endif
-
 } // namespace
 
 // 1 when the work was launched on k_trace_blob, 0 when it does not qualify (the caller falls back to k_trace)
@@ -867,10 +617,6 @@ int launchTraceBlobFast(const TraceWork & w, int bvhDepth, cudaStream_t st)
   const dim3 grid((tilesX + warps - 1) / warps, (uint32_t)((rows + BLOB_TILE_H - 1) / BLOB_TILE_H));
   const unsigned char * blob = reinterpret_cast<const unsigned char *>(w.sceneBlob);
   const uint32_t y0 = (uint32_t)(fp.p0 / fp.W), y1 = (uint32_t)(fp.p1 / fp.W);
-#if RFX_BLOB_COMPACT
-  if (fp.sampleNum == 1 && !fp.jitter && w.argbOut && !w.image) k_trace_blob_compact<<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1);
-  else
-#endif
   if (fp.sampleNum == 1 && !fp.jitter) k_trace_blob<false><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.image);
   else k_trace_blob<true><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.image);
   return 1;

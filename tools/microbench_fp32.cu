@@ -34,6 +34,13 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float * out, float 
       if (MODE == 10) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pb));
       if (MODE == 11) { x[i] = __fmul_rn(x[i], a); p[i] = p[i] * 6364136223846793005ull + 1442695040888963407ull; }   // FMUL + 64-bit IMAD mix
       if (MODE == 12) { asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pa)); x[i] = __fadd_rn(x[i], b); }   // packed mul + scalar add
+      // MODE 5 above is NOT an un-fused mix: ptxas contracts the dependent mul.rn.f32x2 -> add.rn.f32x2 pair into FFMA2 (cuobjdump shows
+      // 512 FFMA2 and no FMUL2/FADD2 in k<5>), also with --fmad=false.  The modes below keep the two packed ops on INDEPENDENT chains
+      // (even i: multiply chain, odd i: add chain), which ptxas cannot contract: that is the real FMUL2 + FADD2 mix.
+      if (MODE == 13) { if (i & 1) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pb)); else asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pa)); }
+      if (MODE == 14) { if (i & 1) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pb)); else x[i] = __fmul_rn(x[i], a); }   // scalar mul + packed add
+      if (MODE == 15) { if (i & 1) x[i] = __fadd_rn(x[i], b); else asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pa)); }   // packed mul + scalar add, independent
+      if (MODE == 16) { if (i & 1) x[i] = __fadd_rn(x[i], b); else x[i] = __fmul_rn(x[i], a); }                                          // scalar mul + scalar add, independent
     }
   }
   float s = 0;
@@ -75,12 +82,16 @@ int main()
   run<2>("fadd", 1, 1, sms, 8);
   run<3>("fmul", 1, 1, sms, 8);
   run<4>("ffma2 (f32x2)", 1, 4, sms, 8);
-  run<5>("fmul2+fadd2 (f32x2)", 2, 2, sms, 8);
+  run<5>("dependent mul.rn.f32x2 -> add.rn.f32x2 (ptxas emits FFMA2: NOT un-fused)", 2, 2, sms, 8);
   run<6>("div.rn", 1, 1, sms, 8);
   run<7>("sqrt.rn+fadd", 1, 1, sms, 8);
   run<8>("div.approx", 1, 1, sms, 8);
   run<9>("fmul2 only (f32x2)", 1, 2, sms, 8);
   run<10>("fadd2 only (f32x2)", 1, 2, sms, 8);
   run<12>("fmul2 + scalar fadd", 2, 1.5, sms, 8);
+  run<13>("fmul2 | fadd2 on independent chains (true un-fused packed mix)", 1, 2, sms, 8);
+  run<14>("fmul | fadd2 on independent chains", 1, 1.5, sms, 8);
+  run<15>("fmul2 | fadd on independent chains", 1, 1.5, sms, 8);
+  run<16>("fmul | fadd on independent chains", 1, 1, sms, 8);
   return 0;
 }
