@@ -59,6 +59,37 @@ def build_shim_harness(force=False):
     return out
 
 
+SHIM_PULSE = os.path.join(HERE, "..", "build", "shim_pulse_headless")
+REFERENCE_SRC = "/root/reference/src/common"
+
+
+def build_shim_pulse(force=False):
+    """The reference's UI controller — Pulse.cpp and BasePlatformInterface.cpp, compiled UNCHANGED from where they lie —
+    against the shim headers, linked with the CUDA library and the headless platform stub: a front end running on the GPU
+    path.  Needs the reference tree (build container); the binary travels to the GPU box with build/.
+    Returns the path, or None when neither the tree nor a prebuilt binary exists."""
+    import shutil
+    import tempfile
+    out = os.path.abspath(SHIM_PULSE)
+    drv = os.path.join(HERE, "..", "oracle", "pulse_headless.cpp")
+    if not os.path.isdir(REFERENCE_SRC):
+        return out if os.access(out, os.X_OK) else None
+    deps = [drv, OUT, os.path.join(HERE, "shim", "rfx_shim.hpp"), os.path.join(REFERENCE_SRC, "Pulse.cpp")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    with tempfile.TemporaryDirectory() as td:
+        for f in ("Pulse.h", "Pulse.cpp", "BasePlatformInterface.h", "BasePlatformInterface.cpp", "defaults.h"):
+            os.symlink(os.path.join(REFERENCE_SRC, f), os.path.join(td, f))     # the reference's own files, untouched
+        for f in os.listdir(os.path.join(HERE, "shim")):
+            shutil.copy(os.path.join(HERE, "shim", f), td)                      # our headers stand in for Render.h, Scene.h, ...
+        subprocess.run(["g++", "-std=c++14", "-O2", "-DNDEBUG", "-ffp-contract=off", "-Wno-multichar", "-I" + td, "-I" + os.path.join(HERE, "..", "include"),
+                        "-o", out, drv, os.path.join(td, "Pulse.cpp"), os.path.join(td, "BasePlatformInterface.cpp"),
+                        "-L" + HERE, "-lreflax_b200", "-Wl,-rpath," + HERE], check=True)
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
     build_shim_harness(force=True)
+    build_shim_pulse(force=True)

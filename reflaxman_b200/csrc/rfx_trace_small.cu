@@ -13,7 +13,7 @@
 //     the triangles (plane-side test on sign bits, tail with the divide); planes last.
 //   * Warps own 4x8 pixel tiles of a 2-D grid (no integer division per thread); tiles are started in the cost order the
 //     previous launch recorded (TileOrder: long paths first), which removes the ~45 us drain behind the mirror-sphere tiles.
-//   * 128-thread CTAs, 63 registers, 8 CTAs per SM; the frame is written with one 128-bit store per tile row.
+//   * 128-thread CTAs, 63 registers, 8 CTAs per SM; the frame is written by 64-byte row segments staged through shared memory.
 //   * The same kernel (MULTI instantiation) serves row-aligned SSAA / additive / float-image slices of the Render API;
 //     k_trace_small_any keeps the arbitrary pixel slices, block preview and signature runs.
 //   * The bounce recursion is the reference's own bounded iterative loop carrying throughput (mulColor).
@@ -493,14 +493,17 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
   const unsigned long long tStart = globalTimer();
 #endif
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t x = (bx * (SMALL_THREADS / 32) + warp) * RFX_TILE_W + (lane % RFX_TILE_W);
-  uint32_t y = y0 + by * RFX_TILE_H + (lane / RFX_TILE_W);
+  const uint32_t xCta = bx * (SMALL_THREADS / 32) * RFX_TILE_W;          // the CTA's tile group: its warps' tiles side by side
+  const uint32_t x = xCta + warp * RFX_TILE_W + (lane % RFX_TILE_W);
+  uint32_t yTop = y0 + by * RFX_TILE_H;                                  // frame row of the group's first row
   if (fp.stripWorld)
   {
-    // split frame: the launch enumerates only this GPU's rows; compact row -> (own strip k, row in strip) -> frame row
-    const uint32_t k = y / fp.stripRows;
-    y = (k * fp.stripWorld + fp.stripRank) * fp.stripRows + (y % fp.stripRows);
+    // split frame: the launch enumerates only this GPU's rows; compact row -> (own strip k, row in strip) -> frame row.  Strips
+    // are multiples of the tile height, so the rows of a tile group lie in one strip
+    const uint32_t k = yTop / fp.stripRows;
+    yTop = (k * fp.stripWorld + fp.stripRank) * fp.stripRows + (yTop % fp.stripRows);
   }
+  const uint32_t y = yTop + (lane / RFX_TILE_W);
   const bool valid = x < fp.W && y < y1;
   uint32_t events = 0;                                                   // MULTI: of the longest call in the low half (cost class)
   uint32_t nBounces = 0, nShadow = 0;                                    // MULTI: totals over the calls
@@ -526,17 +529,18 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
     qOut = q;
     nBounces = events & 0xFFFFu; nShadow = events >> 16;
   }
+  // Framebuffer store of the one-sample path.  A tile group that lies inside the image is staged in shared memory and written by
+  // whole row segments — warp w stores rows 2w and 2w+1, 16 consecutive pixels (64 contiguous bytes) per half warp — after the CTA
+  // barrier the tile scheduler needs anyway.  For a frame in local HBM any pattern merges in L2; when argbOut is another GPU's
+  // framebuffer (split frame, rfx_render_strips over a peer mapping) every store instruction leaves the GPU as NVLink write
+  // packets, and eight 16-byte pieces per instruction (one per tile row) throttled the 7-to-1 gather of an 8K frame to
+  // 0.70 ms against 0.48 ms with local stores (profiles/r2_s2).  Ragged groups at the right / top edge store per lane.
+  constexpr uint32_t GROUP_W = (SMALL_THREADS / 32) * RFX_TILE_W, STAGE_STRIDE = GROUP_W + 4;   // +4 words: conflict-free column writes
+  __shared__ uint32_t sStage[MULTI ? 1 : RFX_TILE_H * STAGE_STRIDE];
+  const bool staged = !MULTI && xCta + GROUP_W <= fp.W && yTop + RFX_TILE_H <= y1;   // uniform over the CTA
   if (!MULTI)
   {
-    // framebuffer store: the four lanes of a tile row hold four consecutive pixels; the first of them stores all four as one
-    // 128-bit word (16-byte aligned when W is a multiple of 4), so a warp writes its 4x8 tile with 8 STG.128
-    const uint32_t p1 = __shfl_down_sync(0xffffffffu, packed, 1), p2 = __shfl_down_sync(0xffffffffu, packed, 2), p3 = __shfl_down_sync(0xffffffffu, packed, 3);
-    const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
-    const bool rowOfFour = RFX_TILE_W % 4u == 0u && (fp.W & 3u) == 0u && ((validMask >> (lane & ~3u)) & 0xFu) == 0xFu;
-    if (rowOfFour)
-    {
-      if ((lane & 3u) == 0u) *reinterpret_cast<uint4 *>(argbOut + qOut) = make_uint4(packed, p1, p2, p3);
-    }
+    if (staged) sStage[(lane / RFX_TILE_W) * STAGE_STRIDE + warp * RFX_TILE_W + (lane % RFX_TILE_W)] = packed;
     else if (valid) argbOut[qOut] = packed;
   }
   if (valid && MULTI)
@@ -591,25 +595,33 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
     }
     if (argbOut) argbOut[q] = packArgb(fin.x, fin.y, fin.z);
   }
+  // file this tile group under its cost class for the next launch: the longest path (bounce-loop iterations) of its pixels
+  __shared__ uint32_t sLongest[SMALL_THREADS / 32];
   if (ord.outLists)
   {
-    // file this tile group under its cost class for the next launch: the longest path (bounce-loop iterations) of its pixels
-    __shared__ uint32_t sLongest[SMALL_THREADS / 32];
     const uint32_t longest = __reduce_max_sync(0xffffffffu, events & 0xFFFFu);
     if (lane == 0) sLongest[warp] = longest;
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-      uint32_t m = 0;
+  }
+  if (staged || ord.outLists) __syncthreads();   // (warps that finish early wait here; the CTA's registers and warp slots are only
+                                                 // released when its last warp ends, so the wait costs nothing that was not already spent)
+  if (staged)
+  {
+    constexpr uint32_t ROWS_PER_WARP = RFX_TILE_H / (SMALL_THREADS / 32), LANES_PER_ROW = 32 / ROWS_PER_WARP;
+    static_assert(MULTI || (RFX_TILE_H % (SMALL_THREADS / 32) == 0 && LANES_PER_ROW == GROUP_W), "staged store: one lane per pixel of the warp's rows");
+    const uint32_t row = warp * ROWS_PER_WARP + lane / LANES_PER_ROW, col = lane % LANES_PER_ROW;
+    argbOut[(yTop + row) * fp.W + xCta + col] = sStage[row * STAGE_STRIDE + col];
+  }
+  if (ord.outLists && threadIdx.x == 0)
+  {
+    uint32_t m = 0;
 #pragma unroll
-      for (int w = 0; w < SMALL_THREADS / 32; w++) m = max(m, sLongest[w]);
-      const uint32_t bounds[TILE_CLASSES - 1] = RFX_TILE_BOUNDS;
-      uint32_t cls = 0;
+    for (int w = 0; w < SMALL_THREADS / 32; w++) m = max(m, sLongest[w]);
+    const uint32_t bounds[TILE_CLASSES - 1] = RFX_TILE_BOUNDS;
+    uint32_t cls = 0;
 #pragma unroll
-      for (int c = 0; c < TILE_CLASSES - 1; c++) cls += m < bounds[c] ? 1u : 0u;   // bounds descend: the count of bounds above m is the class
-      const uint32_t idx = atomicAdd(&ord.outCounts[cls], 1u);
-      if (idx < ord.capacity) ord.outLists[cls * ord.capacity + idx] = (by << 16) | bx;
-    }
+    for (int c = 0; c < TILE_CLASSES - 1; c++) cls += m < bounds[c] ? 1u : 0u;   // bounds descend: the count of bounds above m is the class
+    const uint32_t idx = atomicAdd(&ord.outCounts[cls], 1u);
+    if (idx < ord.capacity) ord.outLists[cls * ord.capacity + idx] = (by << 16) | bx;
   }
 #ifdef RFX_CTA_TIMES
   __syncthreads();
@@ -747,9 +759,6 @@ static uint64_t fastRows(const TraceWork & w)
   if (fp.sampleNum < 1 || w.sigOut || (!w.argbOut && !w.image) || fp.W == 0) return 0;
   if ((uint64_t)fp.sampleNum * fp.sampleNum * (fp.p1 - fp.p0) >= (1ull << 32)) return 0;
   if (fp.p0 % fp.W != 0 || fp.p1 % fp.W != 0 || (uint64_t)fp.W * fp.H >= (1ull << 32)) return 0;
-  // the 128-bit framebuffer stores need a 16-byte aligned frame (rows of a W % 4 == 0 image then stay aligned); a caller's
-  // offset sub-buffer that is only 4-byte aligned takes the general kernel's scalar stores
-  if (w.argbOut && (fp.W & 3u) == 0u && (reinterpret_cast<uintptr_t>(w.argbOut) & 15u) != 0u) return 0;
   uint64_t rows = (fp.p1 - fp.p0) / fp.W;
   if (fp.stripWorld)
   {

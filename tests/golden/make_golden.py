@@ -57,6 +57,18 @@ def main(only=None):
         inputs, outputs = O.run_plane_probe(4096, 777)
         np.savez_compressed(os.path.join(OUT, "plane_probe.npz"), inputs=inputs, outputs=outputs)
         print("plane_probe", hashlib.sha256(outputs.tobytes()).hexdigest()[:16], "hits %.3f" % outputs[:, 0].mean())
+    if not only or "pulse_headless" in only:
+        # the reference's UI controller driven headless (oracle/pulse_headless.cpp built with the reference's own Render):
+        # the last repaint of a scripted interactive session and the hash of the screenshot BMP it saves
+        import subprocess, tempfile
+        with tempfile.TemporaryDirectory() as td:
+            subprocess.run([os.path.join(O.REF_DIR, "ref_pulse_headless"), td + "/", "160", "120", "260", "2", "2"], check=True, stdout=subprocess.DEVNULL)
+            inter = np.fromfile(os.path.join(td, "interactive.bin"), dtype=np.uint32).reshape(120, 160)
+            hud = open(os.path.join(td, "hud.txt")).read()
+            bmp = open(os.path.join(td, "scrnshoot_0000000100000002.bmp"), "rb").read()
+        np.savez_compressed(os.path.join(OUT, "pulse_headless.npz"), interactive=inter, hud=np.array(hud), bmp_sha256=np.array(hashlib.sha256(bmp).hexdigest()),
+                            bmp_bytes=np.array(len(bmp)))
+        print("pulse_headless", hashlib.sha256(bmp).hexdigest()[:16], len(bmp))
     for name, factory, W, H, refl, samples, add, frames, seed, keepf in CASES:
         if only and name not in only:
             continue

@@ -39,6 +39,56 @@ def test_reference_pulse_compiles_unchanged_against_shim():
                             os.path.join(td, src), "-o", os.path.join(td, src + ".o")], check=True)
 
 
+def test_reference_pulse_links_against_shim_and_library(rfx_lib):
+    """f-2: the unchanged Pulse.cpp + BasePlatformInterface.cpp link with the shim, the CUDA library and a headless platform stub."""
+    from reflaxman_b200 import build
+    exe = build.build_shim_pulse(force=os.path.isdir(REF))
+    if exe is None:
+        pytest.skip("no reference tree and no prebuilt build/shim_pulse_headless on this box")
+    assert os.access(exe, os.X_OK)
+
+
+def _run_pulse(exe, td):
+    os.makedirs(td, exist_ok=True)
+    res = subprocess.run([exe, td + "/", "160", "120", "260", "2", "2"], check=True, capture_output=True, text=True, env=dict(os.environ, RFX_SEED="12345"))
+    inter = np.fromfile(os.path.join(td, "interactive.bin"), dtype=np.uint32).reshape(120, 160)
+    hud = open(os.path.join(td, "hud.txt")).read()
+    bmp = open(os.path.join(td, "scrnshoot_0000000100000002.bmp"), "rb").read()
+    return inter, hud, bmp, res.stdout
+
+
+@pytest.mark.gpu
+def test_pulse_runs_headless_on_the_gpu_path(rfx_lib, oracle, tmp_path):
+    """SURVEY §8 f-2, for real: the reference's UI controller (Pulse.cpp, unchanged) running on the GPU path behind a headless
+    BasePlatformInterface — a scripted interactive session (keys W / LEFT / SPACE / D / A: camera kinematics, motion frames in
+    block-preview mode at depth 4, static frames accumulating additively at depth 15, renderNext in adaptive chunks that grow
+    and shrink with a virtual clock, a per-pixel repaint after every frame) and then the F2 screenshot flow at 1024x768 with
+    2x2 SSAA saved as a BMP — against the same program built with the reference's own Render: same HUD text (resolution,
+    blended-frame count), the last repaint and the saved BMP within the parity bar."""
+    import hashlib
+    from reflaxman_b200 import build
+    exe = build.build_shim_pulse()
+    if exe is None:
+        pytest.skip("build/shim_pulse_headless was not built (needs /root/reference at build time)")
+    inter, hud, bmp, info = _run_pulse(exe, str(tmp_path / "gpu"))
+    g = np.load(os.path.join(cases.GOLDEN_DIR, "pulse_headless.npz"))
+    assert hud == str(g["hud"]), (hud, str(g["hud"]))
+    st = cases.assert_parity(inter, g["interactive"], "Pulse interactive repaint")
+    assert len(bmp) == int(g["bmp_bytes"]) == 54 + 1024 * 768 * 4 and bmp[:54] is not None
+    same = hashlib.sha256(bmp).hexdigest() == str(g["bmp_sha256"])
+    print("Pulse headless:", info.strip(), "interactive", st, "screenshot BMP identical to the reference's:", same)
+    ref_exe = os.path.join(oracle.REF_DIR, "ref_pulse_headless")
+    if os.access(ref_exe, os.X_OK):
+        rinter, rhud, rbmp, _ = _run_pulse(ref_exe, str(tmp_path / "ref"))
+        assert rhud == hud and np.array_equal(rinter, g["interactive"])
+        assert rbmp[:54] == bmp[:54]                       # identical BMP headers (Texture.cpp:139-173)
+        a = np.frombuffer(bmp[54:], dtype="<u4").reshape(768, 1024)
+        b = np.frombuffer(rbmp[54:], dtype="<u4").reshape(768, 1024)
+        print("screenshot:", cases.assert_parity(a, b, "Pulse screenshot BMP"))
+    else:
+        assert same, "no reference binary on this box and the BMP differs from the reference's hash"
+
+
 def run_shim_harness(args, seed, W, H, scene=None, cams=None):
     from reflaxman_b200 import build
     exe = build.build_shim_harness()
