@@ -13,7 +13,8 @@
 //     the triangles (plane-side test on sign bits, tail with the divide); planes last.
 //   * Warps own 4x8 pixel tiles of a 2-D grid (no integer division per thread); tiles are started in the cost order the
 //     previous launch recorded (TileOrder: long paths first), which removes the ~45 us drain behind the mirror-sphere tiles.
-//   * 128-thread CTAs, 63 registers, 8 CTAs per SM; the frame is written by 64-byte row segments staged through shared memory.
+//   * 128-thread CTAs, 63 registers, 8 CTAs per SM; the frame is written with one 128-bit store per tile row (split frames that
+//     store into another GPU's framebuffer: 64-byte row segments staged through shared memory).
 //   * The same kernel (MULTI instantiation) serves row-aligned SSAA / additive / float-image slices of the Render API;
 //     k_trace_small_any keeps the arbitrary pixel slices, block preview and signature runs.
 //   * The bounce recursion is the reference's own bounded iterative loop carrying throughput (mulColor).
@@ -47,6 +48,9 @@ namespace rfx
 #endif
 #ifndef RFX_SMALL_THREADS
 #define RFX_SMALL_THREADS 128
+#endif
+#ifndef RFX_STRIP_STAGING
+#define RFX_STRIP_STAGING 1        // split frames: 64-byte row-segment stores staged through shared memory (0: the A/B arm, direct 16-byte stores)
 #endif
 #ifndef RFX_SMALL_MINBLOCKS
 #define RFX_SMALL_MINBLOCKS 8      // fast kernel: 64 registers, no spills, 32 warps per SM
@@ -529,19 +533,33 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
     qOut = q;
     nBounces = events & 0xFFFFu; nShadow = events >> 16;
   }
-  // Framebuffer store of the one-sample path.  A tile group that lies inside the image is staged in shared memory and written by
-  // whole row segments — warp w stores rows 2w and 2w+1, 16 consecutive pixels (64 contiguous bytes) per half warp — after the CTA
-  // barrier the tile scheduler needs anyway.  For a frame in local HBM any pattern merges in L2; when argbOut is another GPU's
-  // framebuffer (split frame, rfx_render_strips over a peer mapping) every store instruction leaves the GPU as NVLink write
-  // packets, and eight 16-byte pieces per instruction (one per tile row) throttled the 7-to-1 gather of an 8K frame to
-  // 0.70 ms against 0.48 ms with local stores (profiles/r2_s2).  Ragged groups at the right / top edge store per lane.
+  // Framebuffer store of the one-sample path.
+  //  * Frame in local HBM: the four lanes of a tile row hold four consecutive pixels; the first of them stores all four as one
+  //    128-bit word (16-byte aligned when W is a multiple of 4 and the frame is), so a warp writes its 4x8 tile with 8 STG.128;
+  //    L2 merges them into lines.
+  //  * Split frame (rfx_render_strips): argbOut may be ANOTHER GPU's framebuffer (peer mapping), and then every store
+  //    instruction leaves this GPU as NVLink write packets.  Eight 16-byte pieces per instruction (one per tile row) throttled
+  //    the 7-to-1 gather of an 8K frame to 0.70 ms against 0.48 ms with local stores (profiles/r2_s2), so a tile group that lies
+  //    inside the image is staged in shared memory and written by whole row segments — warp w stores rows 2w and 2w+1, 16
+  //    consecutive pixels (64 contiguous bytes) per half warp — after the CTA barrier the tile scheduler needs anyway.
+  //    (For local frames the staging costs 0.8 % — measured — so they keep the direct stores.)
   constexpr uint32_t GROUP_W = (SMALL_THREADS / 32) * RFX_TILE_W, STAGE_STRIDE = GROUP_W + 4;   // +4 words: conflict-free column writes
   __shared__ uint32_t sStage[MULTI ? 1 : RFX_TILE_H * STAGE_STRIDE];
-  const bool staged = !MULTI && xCta + GROUP_W <= fp.W && yTop + RFX_TILE_H <= y1;   // uniform over the CTA
+  const bool staged = RFX_STRIP_STAGING && !MULTI && fp.stripWorld != 0u && xCta + GROUP_W <= fp.W && yTop + RFX_TILE_H <= y1;   // uniform over the CTA
   if (!MULTI)
   {
     if (staged) sStage[(lane / RFX_TILE_W) * STAGE_STRIDE + warp * RFX_TILE_W + (lane % RFX_TILE_W)] = packed;
-    else if (valid) argbOut[qOut] = packed;
+    else
+    {
+      const uint32_t p1 = __shfl_down_sync(0xffffffffu, packed, 1), p2 = __shfl_down_sync(0xffffffffu, packed, 2), p3 = __shfl_down_sync(0xffffffffu, packed, 3);
+      const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
+      const bool rowOfFour = RFX_TILE_W % 4u == 0u && (fp.W & 3u) == 0u && ((validMask >> (lane & ~3u)) & 0xFu) == 0xFu;
+      if (rowOfFour)
+      {
+        if ((lane & 3u) == 0u) *reinterpret_cast<uint4 *>(argbOut + qOut) = make_uint4(packed, p1, p2, p3);
+      }
+      else if (valid) argbOut[qOut] = packed;
+    }
   }
   if (valid && MULTI)
   {
@@ -759,6 +777,9 @@ static uint64_t fastRows(const TraceWork & w)
   if (fp.sampleNum < 1 || w.sigOut || (!w.argbOut && !w.image) || fp.W == 0) return 0;
   if ((uint64_t)fp.sampleNum * fp.sampleNum * (fp.p1 - fp.p0) >= (1ull << 32)) return 0;
   if (fp.p0 % fp.W != 0 || fp.p1 % fp.W != 0 || (uint64_t)fp.W * fp.H >= (1ull << 32)) return 0;
+  // the 128-bit framebuffer stores need a 16-byte aligned frame (rows of a W % 4 == 0 image then stay aligned); a caller's
+  // offset sub-buffer that is only 4-byte aligned takes the general kernel's scalar stores
+  if (w.argbOut && (fp.W & 3u) == 0u && (reinterpret_cast<uintptr_t>(w.argbOut) & 15u) != 0u) return 0;
   uint64_t rows = (fp.p1 - fp.p0) / fp.W;
   if (fp.stripWorld)
   {
