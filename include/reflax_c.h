@@ -162,11 +162,14 @@ RFX_API int rfx_enable_profiling(rfx_ctx * ctx, int on);
 /* tuning / test hook; results never depend on an option.  "max_calls_per_launch": Scene::trace calls one random-stream pass and
  * one trace launch may cover (default 2^25 = 128 MB of ranked states; large SSAA factors and 8K frames are rendered in chunks of
  * this many calls — tests lower it to drive the chunk loop at small sizes).  "copy_streams": device->host streams
- * rfx_render_frames alternates between (1 or 2, default 1). */
+ * rfx_render_frames alternates between (1 or 2, default 1).  "blob_wavefront": scenes that do not fit the constant bank render
+ * their one-sample ARGB frames of reflection depth >= 4 with a two-kernel wavefront — the first k segments of every path in pixel
+ * tiles, the rest from a path queue (k = the value, default 2; 0 = the single tile kernel).  "blob_smem_bvh": the queue-driven
+ * kernel keeps a small sphere hierarchy in shared memory (default 1).  Frames are bit-identical under every setting. */
 RFX_API int rfx_set_option(rfx_ctx * ctx, const char * name, int64_t value);
 /* kernel selection: 0 = automatic (constant-bank kernel when the scene fits, the general blob kernel otherwise),
- * 1 = constant-bank kernel if it fits, 2 = always the blob kernels (batch kernel for row-aligned one-sample ARGB slices, the
- * general one otherwise), 3 = always the general blob kernel.  Results are identical; tests use it. */
+ * 1 = constant-bank kernel if it fits, 2 = always the blob kernels (tile / wavefront kernels for row-aligned slices, the general
+ * one otherwise), 3 = always the general blob kernel.  Results are identical; tests use it. */
 RFX_API int rfx_force_path(rfx_ctx * ctx, int path);
 /* acceleration structure of the general blob kernel: 0 = automatic (bounding-volume hierarchy over the spheres when there are
  * more than 32), 1 = always, 2 = never (the reference's brute-force list walk).  Results are identical; tests compare them. */

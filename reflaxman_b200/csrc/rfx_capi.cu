@@ -136,11 +136,13 @@ struct rfx_ctx
   bool tileHistory = false;                 // the other set holds the order recorded by the previous launch ...
   uint64_t tileKey[4] = { 0, 0, 0, 0 };     // ... over this grid (image size, row range, strip split)
   bool tileOrdering = true;
-  int forcePath = 0;                        // 0 auto, 1 small (constant bank), 2 blob kernels, 3 blob, general kernel only — tests exercise all
+  int forcePath = 0;                        // 0 auto, 1 constant bank, 2 blob kernels, 3 blob, general kernel (k_trace_blob_any) only — tests exercise all
   float * dLut = nullptr;
   float4 * dBvhNodes = nullptr; size_t bvhNodesCap = 0;   // big scenes only (see buildBvh)
   int * dBvhPrims = nullptr; size_t bvhPrimsCap = 0;
   int bvhDepth = 0;                         // depth of the hierarchy in dBvhNodes (0: none)
+  uint32_t bvhFloat4 = 0;                   // SceneHeader::bvhFloat4 of the uploaded blob
+  bool blobSmemBvh = true;                  // rfx_set_option "blob_smem_bvh"
   int bvhMode = 0;                          // 0 auto (spheres > 32), 1 always, 2 never — tests compare both
 
   // ---- camera + render state (reference Render.h:9-27)
@@ -168,6 +170,10 @@ struct rfx_ctx
   uint32_t * dResolve = nullptr; size_t resolveCap = 0;   // K3 output of the Render-API read path (its own buffer and capacity)
   uint64_t maxCallsPerLaunch = 1ull << 25;    // bounds the ranked-state scratch (128 MB) for huge SSAA factors / 8K frames
   float bvhReach[6] = { 0, 0, 0, 0, 0, 0 };   // box of ray origins the hierarchy's margins were sized for (lo xyz, hi xyz)
+  // path queue of the blob scenes' wavefront kernel pair (rfx_trace_blob.cu): 64-byte records + {count, cursor}
+  uint4 * dQueue = nullptr; size_t queueCap = 0;   // in uint4 units (4 per record)
+  uint32_t * dQueueCtl = nullptr;
+  int blobWavefront = 2;                      // rfx_set_option "blob_wavefront": 0 off, k > 0: the tile kernel of the wavefront renders k segments
   cudaEvent_t evRendered[FRAME_SLOTS] = { nullptr, nullptr, nullptr, nullptr }, evCopied[FRAME_SLOTS] = { nullptr, nullptr, nullptr, nullptr };
 
   // ---- counters
@@ -272,12 +278,13 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
   h.offTex = (uint32_t)off; off = align16(off + sizeof(TexRef) * ctx->tex.size());
   h.bytes = (uint32_t)off;
   h.byteLut = ctx->dLut;
-  h.bvhNodes = nullptr;
   h.bvhPrims = nullptr;
   h.bvhLeafSph = nullptr;
   h.bvhPairs = nullptr;
   h.bvhRoot = 0;
+  h.bvhFloat4 = 0;
   ctx->bvhDepth = 0;
+  ctx->bvhFloat4 = 0;
   const bool wantBvh = ctx->bvhMode == 1 ? !sph.empty() : ctx->bvhMode == 2 ? false : sph.size() > 32;
   if (wantBvh)
   {
@@ -326,16 +333,16 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
     std::vector<BvhNode> nodes;
     int maxDepth = 0;
     buildBvhRec(nodes, prims, 0, (int)prims.size(), 0, maxDepth);
-    if (maxDepth < 30)   // traversal stack is 32 deep; a median split of < 2^30 spheres never gets here
+    if (maxDepth <= BLOB_MAX_BVH_DEPTH)   // the traversal stacks hold 24 entries; a median split of the <= 12 800 spheres a 200 KB blob can carry is 13 deep
     {
-      // leaves are padded to 4 slots: bvhPrims[4 * leaf + k] = sphere index (k < count), and — for the batch kernel, which tests a
-      // whole leaf without indirection — bvhLeafSph[4 * leaf + k] = that sphere's (cx, cy, cz, r^2), NaN in the unused slots
+      // The device form, one allocation: leaf records — every leaf is 4 slots of (cx, cy, cz, r^2), NaN in the unused ones, so a
+      // whole leaf is tested without indirection — then the "pair nodes": an inner node carries both children's boxes,
+      // {lo_a.xyz, ref_a} {hi_a.xyz, ref_b} {lo_b.xyz, -} {hi_b.xyz, -}, ref >= 0: pair node index, ref < 0: ~(first slot of a leaf).
+      // bvhPrims[4 * leaf + k] = position of that slot's sphere in the sorted sphere array (materials, tie-break order).
       size_t nLeaves = 0;
       for (const BvhNode & n : nodes) nLeaves += n.b < 0;
-      // and — also for the batch kernel — the inner nodes once more with both children's boxes side by side ("pair nodes"):
-      // {lo_a.xyz, ref_a} {hi_a.xyz, ref_b} {lo_b.xyz, -} {hi_b.xyz, -}, ref >= 0: pair node index, ref < 0: ~(first slot of a leaf)
       const size_t nInner = nodes.size() - nLeaves;
-      std::vector<float4> packed(nodes.size() * 2 + nLeaves * 4 + nInner * 4);
+      std::vector<float4> packed(nLeaves * 4 + nInner * 4);
       std::vector<int> ref(nodes.size());
       {
         int inner = 0, lf = 0;
@@ -346,9 +353,9 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
       size_t leaf = 0;
       for (size_t i = 0; i < nodes.size(); i++)
       {
-        int a = nodes[i].a;
         if (nodes[i].b < 0)
         {
+          const int a = nodes[i].a;
           for (int k = 0; k < 4; k++)
           {
             float4 s4 = make_float4(qnan, qnan, qnan, qnan);
@@ -358,21 +365,18 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
               s4 = make_float4(o->center[0], o->center[1], o->center[2], o->sqRadius);
               order[4 * leaf + k] = prims[a + k].index;
             }
-            packed[nodes.size() * 2 + 4 * leaf + k] = s4;
+            packed[4 * leaf + k] = s4;
           }
-          a = (int)(4 * leaf++);
+          leaf++;
         }
         else
         {
           const BvhNode & ca = nodes[nodes[i].a], & cb = nodes[nodes[i].b];
-          float4 * w = &packed[nodes.size() * 2 + nLeaves * 4 + 4 * (size_t)ref[i]];
+          float4 * w = &packed[nLeaves * 4 + 4 * (size_t)ref[i]];
           w[0] = make_float4(ca.lo[0], ca.lo[1], ca.lo[2], 0.0f); w[1] = make_float4(ca.hi[0], ca.hi[1], ca.hi[2], 0.0f);
           w[2] = make_float4(cb.lo[0], cb.lo[1], cb.lo[2], 0.0f); w[3] = make_float4(cb.hi[0], cb.hi[1], cb.hi[2], 0.0f);
           memcpy(&w[0].w, &ref[nodes[i].a], 4); memcpy(&w[1].w, &ref[nodes[i].b], 4);
         }
-        float4 lo4 = make_float4(nodes[i].lo[0], nodes[i].lo[1], nodes[i].lo[2], 0.0f), hi4 = make_float4(nodes[i].hi[0], nodes[i].hi[1], nodes[i].hi[2], 0.0f);
-        memcpy(&lo4.w, &a, 4); memcpy(&hi4.w, &nodes[i].b, 4);
-        packed[2 * i] = lo4; packed[2 * i + 1] = hi4;
       }
       int rc;
       if ((rc = ensure(ctx, ctx->dBvhNodes, ctx->bvhNodesCap, packed.size())) != RFX_OK) return rc;
@@ -381,11 +385,13 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
       CK(cudaMemcpyAsync(ctx->dBvhPrims, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
       CK(cudaStreamSynchronize(st));
       ctx->stats.h2d_bytes += packed.size() * sizeof(float4) + order.size() * sizeof(int);
-      h.bvhNodes = ctx->dBvhNodes;
       ctx->bvhDepth = maxDepth;
       h.bvhPrims = ctx->dBvhPrims;
-      h.bvhLeafSph = ctx->dBvhNodes + nodes.size() * 2;
+      h.bvhLeafSph = ctx->dBvhNodes;
       h.bvhPairs = h.bvhLeafSph + nLeaves * 4;
+      h.bvhRoot = ref[0];
+      h.bvhFloat4 = (uint32_t)((nLeaves + nInner) * 4);
+      ctx->bvhFloat4 = h.bvhFloat4;
       h.bvhRoot = ref[0];
     }
   }
@@ -584,8 +590,20 @@ int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, boo
         ctx->stats.kernel_launches += nl;
         (fastGrid ? ctx->stats.launches_small_fast : ctx->stats.launches_small_any) += nl;
       }
-      else if (ctx->forcePath != 3 && launchTraceBlobFast(w, ctx->bvhDepth, st)) { ctx->stats.kernel_launches += 1; ctx->stats.launches_blob_fast += 1; }
-      else { const int nl = launchTrace(w, st); ctx->stats.kernel_launches += nl; ctx->stats.launches_blob_any += nl; }
+      else
+      {
+        const uint64_t wavePixels = (ctx->blobWavefront && ctx->forcePath != 3) ? blobWavePixels(w) : 0;
+        if (wavePixels)
+        {
+          if ((rc = ensure(ctx, ctx->dQueue, ctx->queueCap, (size_t)wavePixels * 4)) != RFX_OK) return rc;   // 64-byte records
+          if (!ctx->dQueueCtl) CK(cudaMalloc((void **)&ctx->dQueueCtl, 2 * sizeof(uint32_t)));
+        }
+        int nl = ctx->forcePath == 3 ? 0 : launchTraceBlobFast(w, st, wavePixels ? ctx->dQueue : nullptr, ctx->dQueueCtl, (uint32_t)ctx->prop.multiProcessorCount * 8u,
+                                                               ctx->blobWavefront, ctx->blobSmemBvh ? ctx->bvhFloat4 : 0u);
+        if (nl) ctx->stats.launches_blob_fast += nl;
+        else { nl = launchTraceBlobAny(w, st); ctx->stats.launches_blob_any += nl; }
+        ctx->stats.kernel_launches += nl;
+      }
       if (evB) CK(cudaEventRecord(evB, st));
       CK(cudaGetLastError());
       ctx->stats.samples += nCalls;
@@ -687,7 +705,7 @@ void rfx_destroy(rfx_ctx * ctx)
   cudaFree(ctx->dRngPrefix); cudaFree(ctx->dRngLocate); cudaFree(ctx->dSampleStates); cudaFree(ctx->dStatus);
   cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dBvhNodes); cudaFree(ctx->dBvhPrims); cudaFree(ctx->dTileLists[0]); cudaFree(ctx->dTileLists[1]); cudaFree(ctx->dTileCounts);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
-  cudaFree(ctx->dResolve);
+  cudaFree(ctx->dResolve); cudaFree(ctx->dQueue); cudaFree(ctx->dQueueCtl);
   for (int i = 0; i < rfx_ctx::FRAME_SLOTS; i++)
   {
     cudaFree(ctx->dFrame[i]);
@@ -1206,7 +1224,7 @@ int rfx_trace_rays(rfx_ctx * ctx, int n, const float * origins, const float * ra
   CK(cudaMemcpyAsync(dO, origins, (size_t)n * 12, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dR, rays, (size_t)n * 12, cudaMemcpyHostToDevice, st));
   ctx->stats.h2d_bytes += (uint64_t)n * 24;
-  ctx->stats.kernel_launches += launchTraceRays(ctx->dBlob, ctx->blobBytes, n, dO, dR, reflect_num, ctx->dSampleStates, dC, ctx->dCounters, st);
+  ctx->stats.kernel_launches += launchTraceBlobRays(ctx->dBlob, n, dO, dR, reflect_num, ctx->dSampleStates, dC, ctx->dCounters, st);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(rgb, dC, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -1418,6 +1436,17 @@ int rfx_set_option(rfx_ctx * ctx, const char * name, int64_t value)
   {
     if (value < 1) return fail(ctx, RFX_ERR_ARG, "rfx_set_option: max_calls_per_launch must be >= 1");
     ctx->maxCallsPerLaunch = (uint64_t)value;
+    return RFX_OK;
+  }
+  if (!strcmp(name, "blob_wavefront"))
+  {
+    if (value < 0 || value > 64) return fail(ctx, RFX_ERR_ARG, "rfx_set_option: blob_wavefront must be 0 (off) or the number of first segments (1..64)");
+    ctx->blobWavefront = (int)value;
+    return RFX_OK;
+  }
+  if (!strcmp(name, "blob_smem_bvh"))
+  {
+    ctx->blobSmemBvh = value != 0;
     return RFX_OK;
   }
   if (!strcmp(name, "copy_streams"))

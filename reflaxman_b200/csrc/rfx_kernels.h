@@ -1,4 +1,5 @@
-// rfx_kernels.h — launch interface between the C-ABI host layer (rfx_capi.cu) and the sm_100a kernels (rfx_kernels.cu).
+// rfx_kernels.h — launch interface between the C-ABI host layer (rfx_capi.cu) and the sm_100a kernels (rfx_kernels.cu: K1 and K3;
+// rfx_trace_small.cu, rfx_trace_blob.cu: K2).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -76,19 +77,27 @@ struct TraceWork
   unsigned long long * counters;// device [32][2] striped {bounces, shadowRays}
   TileOrder order;              // fast constant-bank kernel only
 };
-int launchTrace(const TraceWork & w, cudaStream_t st);                              // any scene: blob in global memory, BVH over the spheres
-// blob scenes, row-aligned slices (one sample per pixel, grid SSAA, additive jitter; ARGB and/or float image out): rfx_trace_blob.cu.  Returns 0 without launching when
-// the work does not qualify (the caller uses launchTrace); bvhDepth = depth of the hierarchy the blob points at (0: none)
-int launchTraceBlobFast(const TraceWork & w, int bvhDepth, cudaStream_t st);
+// blob scenes (rfx_trace_blob.cu).  launchTraceBlobFast: row-aligned slices (one sample per pixel, grid SSAA, additive jitter; ARGB
+// and/or float image out); one-sample ARGB slices run as a wavefront pair when queue scratch is given (persistentCtas: grid of
+// the queue-driven kernel in 128-thread CTAs).  Returns the
+// number of kernels launched, 0 when the work does not qualify (the caller uses launchTraceBlobAny).  BVH depth is bounded by the host
+// (BLOB_MAX_BVH_DEPTH): the traversal stack holds 24 entries per thread.
+constexpr int BLOB_MAX_BVH_DEPTH = 22;
+uint64_t blobWavePixels(const TraceWork & w);
+constexpr int BLOB_WAVE_MIN_DEPTH = 4;       // shallower reflection limits render with the single tile kernel (the wavefront gains from depth 4 on)
+// queueRecords: blobWavePixels(w) records of 64 bytes, queueCounters: 2 words
+int launchTraceBlobFast(const TraceWork & w, cudaStream_t st, void * queueRecords = nullptr, uint32_t * queueCounters = nullptr, uint32_t persistentCtas = 0,
+                        int firstSegments = 2,    // segments the tile kernel renders before it queues a path (0: no wavefront)
+                        uint32_t bvhFloat4 = 0);  // SceneHeader::bvhFloat4 of the blob (0: no hierarchy): small hierarchies are copied to shared memory
+int launchTraceBlobAny(const TraceWork & w, cudaStream_t st);     // every renderNext mode: ragged slices, block preview, signatures
+// Scene::trace for a list of rays (rfx_trace_rays): rays[i] uses sampleStates[i]
+int launchTraceBlobRays(const void * sceneBlob, int n, const float * origins, const float * rays, int reflNum,
+                        const uint32_t * sampleStates, float * rgbOut, unsigned long long * counters, cudaStream_t st);
 // small scenes: constant-bank resident; *fastGrid (optional) receives the CTA count of the fast kernel's grid, 0 when the
 // general kernel ran (the caller keeps tile-order history only for fast launches)
 int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st, uint32_t * fastGrid = nullptr);
 // CTA count the fast kernel would use for this work, 0 if the work does not qualify for it
 uint32_t fastGridSize(const TraceWork & w);
-
-// Scene::trace for a list of rays (rfx_trace_rays): rays[i] uses sampleStates[i]
-int launchTraceRays(const void * sceneBlob, uint32_t sceneBytes, int n, const float * origins, const float * rays, int reflNum,
-                    const uint32_t * sampleStates, float * rgbOut, unsigned long long * counters, cudaStream_t st);
 
 // ---- K3: resolve (imagePixel + argb) ---------------------------------------------------------------------------
 int launchResolve(const float * image, uint64_t nPixels, int additiveCounter, float * rgbfOut, uint32_t * argbOut, cudaStream_t st);

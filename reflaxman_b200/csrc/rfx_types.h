@@ -60,11 +60,11 @@ struct SceneHeader
   uint32_t offLights, offSpheres, offTris, offPlanes, offMats, offTex;   // byte offsets inside the blob
   uint32_t bytes;                   // blob size
   const float * byteLut;            // 256 floats: float(i) / 255.0f computed on the host (reference Color.cpp:11-13)
-  const float4 * bvhNodes;          // big scenes: 2 float4 per node {min.xyz, a} {max.xyz, b}; b < 0: leaf of -b prims starting at slot a; else children a, b
-  const int * bvhPrims;             // sphere indices (sorted-array positions) referenced by the leaves, 4 slots per leaf (-1 = unused)
-  const float4 * bvhPairs;          // inner nodes with both children's boxes: 4 float4 per node {lo_a, ref_a} {hi_a, ref_b} {lo_b, -} {hi_b, -}; ref >= 0 pair node, < 0 ~leaf slot
+  const int * bvhPrims;             // big scenes: sphere indices (sorted-array positions) of the leaf slots, 4 slots per leaf (-1 = unused)
+  const float4 * bvhPairs;          // NULL: no hierarchy (list walk).  Inner nodes with both children's boxes: 4 float4 per node {lo_a, ref_a} {hi_a, ref_b} {lo_b, -} {hi_b, -}; ref >= 0 pair node, < 0 ~leaf slot
   int bvhRoot;                      // ref of the root (a pair node, or a leaf when there are <= 4 spheres)
   const float4 * bvhLeafSph;        // the same slots as (cx, cy, cz, r^2), NaN = unused: a leaf is 4 contiguous records
+  uint32_t bvhFloat4;               // float4 count of [leaf records | pair nodes], contiguous from bvhLeafSph (what a CTA copies to shared memory)
 };
 
 // Small scenes travel as a kernel parameter (constant bank): see rfx_trace_small.cu

@@ -4,7 +4,7 @@ round-1 advisor findings.  Everything goes through the C ABI (ctypes).
   * config 3 (7680x4320, depth 20): whole frame == the same frame rendered in chunks == the 2- and 3-way interleaved-strip
     split == the oracle (and the unmodified reference binary / its committed hash): exercises q < 2^32 pixel indexing, tile
     edges, K1 block ownership under strips and the 540-row tile grid at full size;
-  * config 4 (1024 spheres, 3840x2160, depth 8): BVH batch kernel == brute-force list walk == general blob kernel, and the
+  * config 4 (1024 spheres, 3840x2160, depth 8): wavefront kernel pair == tile kernel == brute-force list walk == round-1 general kernel, and the
     multithreaded oracle at 960x540;
   * renderRange's chunk loop (huge SSAA factors): driven at small sizes by lowering "max_calls_per_launch".
 """
@@ -105,13 +105,18 @@ def test_config4_full_size_bvh_equals_list_walk_equals_general_kernel(capi, orac
     cam = S.default_camera()
     scene = cases.config4_scene()
     out = {}
-    for name, path, bvh in (("batch+bvh", 2, 0), ("general+bvh", 3, 0), ("batch+list", 2, 2)):
+    # wave > 0: wavefront pair — the tile kernel for `wave` segments + the queue-driven kernel (hierarchy in shared memory, or, "L1",
+    # read in place); wave 0: the single tile kernel; path 3: the round-1 general kernel
+    for name, path, bvh, wave in (("batch+bvh", 2, 0, 2), ("wave1+bvh", 2, 0, 1), ("wave3+bvh", 2, 0, 3), ("batch+bvh+L1", 2, 0, 2), ("tile+bvh", 2, 0, 0),
+                                  ("general+bvh", 3, 0, 0), ("batch+list", 2, 2, 2)):
         c = _ctx(capi, scene, W, H, seed)
         try:
             c.force_path(path); c.set_bvh_mode(bvh); c.stats_reset()
+            c.set_option("blob_wavefront", wave); c.set_option("blob_smem_bvh", 0 if name.endswith("L1") else 1)
             img = c.render_frames([cam], refl)[0].copy()
             st = c.stats()
-            assert (st["launches_blob_fast"], st["launches_blob_any"]) == ((1, 0) if path == 2 else (0, 1)), (name, st)
+            want = 2 if wave > 0 else 1
+            assert (st["launches_blob_fast"], st["launches_blob_any"]) == ((want, 0) if path == 2 else (0, 1)), (name, st)
             out[name] = (img, st["rays"], st["bounces"], c.get_seeds())
         finally:
             c.close()
@@ -127,7 +132,7 @@ def test_config4_full_size_bvh_equals_list_walk_equals_general_kernel(capi, orac
         c.stats_reset()
         small = c.render_frames([cam], refl)[0]
         st = c.stats()
-        assert st["launches_blob_fast"] == 1
+        assert st["launches_blob_fast"] == 2
         assert st["rays"] == o.counters["rays"] and st["bounces"] == o.counters["bounces"]
         print("config 4 at 960x540 vs oracle:", cases.assert_parity(small, o.resolve()[1], "config 4 vs oracle"))
         c.set_seeds(seed, seed)
@@ -234,7 +239,17 @@ def test_unaligned_device_framebuffer(capi, path):
         c.render_frames_device(capi.pack_cameras([cam]), refl, 1, buf + 4)
         c.synchronize()
         st = c.stats()
-        assert st["launches_small_fast"] + st["launches_blob_fast"] == 0, st
+        # (the blob scenes' wavefront pair stores 4-byte words and takes any frame; its single tile kernel, like the constant-bank
+        # fast kernel, stores 128-bit words and hands a misaligned frame to the general kernel)
+        assert st["launches_small_fast"] == 0 and (st["launches_blob_fast"] == 0 if path == 1 else st["launches_blob_fast"] > 1), st
+        if path == 2:
+            c.set_option("blob_wavefront", 0)
+            c.set_seeds(3, 3)
+            c.stats_reset()
+            c.render_frames_device(capi.pack_cameras([cam]), refl, 1, buf + 4)
+            c.synchronize()
+            st = c.stats()
+            assert st["launches_blob_fast"] == 0 and st["launches_blob_any"] == 1, st
         got = c.buffer_read(buf, np.zeros(W * H + 4, np.uint32))
         assert got[0] == 0 and np.array_equal(got[1:1 + W * H].reshape(H, W), want)
         c.buffer_free(buf)

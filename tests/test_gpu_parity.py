@@ -175,7 +175,8 @@ def test_bvh_equals_brute_force(capi, oracle, n_side, size, depth):
 @pytest.mark.parametrize("which,size,depth,bvh", [("grid6", (128, 72), 8, 1), ("grid12", (161, 90), 6, 0), ("grid12", (160, 91), 6, 2),
                                                    ("mixed", (250, 131), 12, 0), ("mixed", (64, 40), 12, 1), ("grid2", (64, 40), 6, 1)])
 def test_blob_batch_kernel_equals_general_blob_kernel(capi, oracle, which, size, depth, bvh):
-    """rfx_trace_blob.cu (state machine, shared-memory traversal stack; row-aligned one-sample ARGB slices of blob scenes) against
+    """rfx_trace_blob.cu (state machine, shared-memory traversal stack; row-aligned one-sample ARGB slices of blob scenes: as the
+    wavefront kernel pair and as the single tile kernel) against
     k_trace: identical frames, ray counts and stream position, with and without the hierarchy, widths that are not a multiple of
     the tile width, heights that are not a multiple of the tile height, a hierarchy whose root is a leaf (4 spheres); and both meet the
     parity bar against the oracle."""
@@ -183,18 +184,22 @@ def test_blob_batch_kernel_equals_general_blob_kernel(capi, oracle, which, size,
     scene = _mixed_scene() if which == "mixed" else S.synthetic_scene(int(which[4:]), floor=S.synthetic_texture(64, 64, 3), skybox=S.synthetic_texture(128, 96, 5))
     cams = [S.default_camera(), S.orbit_cameras(7)[3]]
     out = {}
-    for path in (2, 3):
+    for path, wave in ((2, 2), (2, 0), (3, 0)):
         c = capi.Context(0)
         try:
             c.load_scene(scene); c.set_seeds(99, 99); c.set_image_size(W, H)
-            c.force_path(path); c.set_bvh_mode(bvh); c.stats_reset()
+            c.force_path(path); c.set_bvh_mode(bvh); c.set_option("blob_wavefront", wave); c.stats_reset()
             frames = c.render_frames(cams, depth)
             st = c.stats()
-            out[path] = (frames.copy(), st["rays"], st["bounces"], c.get_seeds())
+            # the wavefront (two segments in tiles, the rest in the queue-driven kernel) is two launches per frame, the tile kernel one
+            assert st["launches_blob_fast"] == (0 if path == 3 else len(cams) * (2 if wave else 1)), st
+            out[(path, wave)] = (frames.copy(), st["rays"], st["bounces"], c.get_seeds())
         finally:
             c.close()
-    assert np.array_equal(out[2][0], out[3][0])
-    assert out[2][1:] == out[3][1:]
+    for key in ((2, 0), (3, 0)):
+        assert np.array_equal(out[(2, 2)][0], out[key][0]), key
+        assert out[(2, 2)][1:] == out[key][1:], key
+    out = {2: out[(2, 2)], 3: out[(3, 0)]}
     o = oracle.OracleRender(scene, W, H, seed=99)
     rays = 0
     for k, cam in enumerate(cams):

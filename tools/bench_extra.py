@@ -191,6 +191,10 @@ def config4(env, steps=5, brute=False, depths=(1, 2, 3, 4, 5, 6, 7, 8), fp32_pea
     ctx.load_scene(S.synthetic_scene(32, floor=S.synthetic_texture(1024, 1024, 11), skybox=S.synthetic_texture(2048, 1536, 7)))
     ctx.set_image_size(Wd, Hd); ctx.set_seeds(12345, 12345)
     ctx.set_bvh_mode(2 if brute else 0)
+    if os.environ.get("RFX_BLOB_WAVEFRONT"):
+        ctx.set_option("blob_wavefront", int(os.environ["RFX_BLOB_WAVEFRONT"]))   # 0 = the single tile kernel (A/B against the wavefront), k = segments in tiles
+    if os.environ.get("RFX_BLOB_SMEM_BVH"):
+        ctx.set_option("blob_smem_bvh", int(os.environ["RFX_BLOB_SMEM_BVH"]))
     if os.environ.get("RFX_FORCE_PATH"):
         ctx.force_path(int(os.environ["RFX_FORCE_PATH"]))   # 3 = general blob kernel only (A/B against the batch kernel)
     out = torch.empty((1, Hd, Wd), dtype=torch.int32, device="cuda")
