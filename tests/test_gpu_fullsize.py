@@ -202,6 +202,32 @@ def test_ssaa16_matches_oracle(capi, oracle):
         c.close()
 
 
+@pytest.mark.parametrize("path", [1, 2], ids=["constbank", "blob"])
+@pytest.mark.parametrize("s,size", [(128, (16, 12)), (256, (8, 6))])
+def test_showcase_ssaa_factors_match_oracle(capi, oracle, s, size, path):
+    """The reference README's showcase is a 128x128-SSAA screenshot and Pulse's menu goes to 256x256 (Pulse.cpp:22-34): 16 384 and
+    65 536 Scene::trace calls per pixel, summed in the reference's ssx-outer / ssy-inner order.  A tiny image keeps the oracle in
+    seconds; with the launch cap at 2^20 calls the 8x6 frame at s = 256 is three chunks of rows."""
+    W, H = size
+    refl, seed = 10, 77
+    cam = S.default_camera()
+    o = oracle.OracleRender(S.default_scene(), W, H, seed=seed).render(cam, refl, s)
+    orgbf, oargb = o.resolve()
+    c = _ctx(capi, S.default_scene(), W, H, seed)
+    try:
+        c.force_path(path)
+        c.set_option("max_calls_per_launch", 1 << 20)
+        c.stats_reset()
+        c.render(cam, refl, s)
+        st = c.stats()
+        assert st["samples"] == W * H * s * s and st["rays"] == o.counters["rays"]
+        assert c.get_seeds()[0] == int(o.seeds[0])
+        cases.assert_parity(c.read_argb(), oargb, "ssaa %d" % s)
+        assert np.max(np.abs(c.read_rgbf() - orgbf)) < 2e-5
+    finally:
+        c.close()
+
+
 # ---------------------------------------------------------------------------------------------- advisor findings (round 1)
 def test_resize_then_read_then_batch_does_not_overrun_frame_slots(capi):
     """render_frames at size A, set_image_size(B > A), read_argb, render_frames at B used to leave two of
