@@ -465,7 +465,7 @@ __device__ __forceinline__ unsigned smId() { unsigned s; asm volatile("mov.u32 %
 // blockIdx.y = tile row, blockIdx.x * warps + warp = tile column.  MULTI = false: one sample per pixel, no jitter, ARGB
 // output only (the bench path).  MULTI = true: the same tiling and scheduling for grid SSAA (Render.cpp:174-196), additive
 // jitter and accumulation, and the float image of the Render API.
-template <int FEAT, bool MULTI>
+template <int FEAT, bool MULTI, bool STRIPS>
 __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS) k_trace_small(const __grid_constant__ SmallScene sc, const __grid_constant__ FrameParams fp,
                                                                const uint32_t * __restrict__ sampleStates, uint32_t * __restrict__ argbOut,
                                                                unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1,
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
   const uint32_t xCta = bx * (SMALL_THREADS / 32) * RFX_TILE_W;          // the CTA's tile group: its warps' tiles side by side
   const uint32_t x = xCta + warp * RFX_TILE_W + (lane % RFX_TILE_W);
   uint32_t yTop = y0 + by * RFX_TILE_H;                                  // frame row of the group's first row
-  if (fp.stripWorld)
+  if (STRIPS)
   {
     // split frame: the launch enumerates only this GPU's rows; compact row -> (own strip k, row in strip) -> frame row.  Strips
     // are multiples of the tile height, so the rows of a tile group lie in one strip
@@ -542,10 +542,11 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
   //    the 7-to-1 gather of an 8K frame to 0.70 ms against 0.48 ms with local stores (profiles/r2_s2), so a tile group that lies
   //    inside the image is staged in shared memory and written by whole row segments — warp w stores rows 2w and 2w+1, 16
   //    consecutive pixels (64 contiguous bytes) per half warp — after the CTA barrier the tile scheduler needs anyway.
-  //    (For local frames the staging costs 0.8 % — measured — so they keep the direct stores.)
+  //    (For local frames the staging costs 0.8 % — measured — so they keep the direct stores: STRIPS is a template parameter and
+  //    the whole-frame instantiations carry none of this.)
   constexpr uint32_t GROUP_W = (SMALL_THREADS / 32) * RFX_TILE_W, STAGE_STRIDE = GROUP_W + 4;   // +4 words: conflict-free column writes
-  __shared__ uint32_t sStage[MULTI ? 1 : RFX_TILE_H * STAGE_STRIDE];
-  const bool staged = RFX_STRIP_STAGING && !MULTI && fp.stripWorld != 0u && xCta + GROUP_W <= fp.W && yTop + RFX_TILE_H <= y1;   // uniform over the CTA
+  __shared__ uint32_t sStage[(MULTI || !STRIPS) ? 1 : RFX_TILE_H * STAGE_STRIDE];
+  const bool staged = RFX_STRIP_STAGING && !MULTI && STRIPS && xCta + GROUP_W <= fp.W && yTop + RFX_TILE_H <= y1;   // uniform over the CTA
   if (!MULTI)
   {
     if (staged) sStage[(lane / RFX_TILE_W) * STAGE_STRIDE + warp * RFX_TILE_W + (lane % RFX_TILE_W)] = packed;
@@ -836,14 +837,22 @@ int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st
         const bool lean = !texels && sc.nP == 0 && sc.nL <= 1;
         const bool multi = fp.sampleNum != 1 || fp.jitter || w.image != nullptr;
         const uint32_t y0 = (uint32_t)(fp.p0 / fp.W), y1 = (uint32_t)(fp.p1 / fp.W);
-        if (lean && !multi)
-          k_trace_small<0, false><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.order, nullptr);
-        else if (!multi)
-          k_trace_small<F_ALL, false><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.order, nullptr);
-        else if (lean)
-          k_trace_small<0, true><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.order, w.image);
+#define RFX_LAUNCH_SMALL(F, M, S, IMG) k_trace_small<F, M, S><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.order, IMG)
+        if (fp.stripWorld)
+        {
+          if (lean && !multi) RFX_LAUNCH_SMALL(0, false, true, nullptr);
+          else if (!multi) RFX_LAUNCH_SMALL(F_ALL, false, true, nullptr);
+          else if (lean) RFX_LAUNCH_SMALL(0, true, true, w.image);
+          else RFX_LAUNCH_SMALL(F_ALL, true, true, w.image);
+        }
         else
-          k_trace_small<F_ALL, true><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.order, w.image);
+        {
+          if (lean && !multi) RFX_LAUNCH_SMALL(0, false, false, nullptr);
+          else if (!multi) RFX_LAUNCH_SMALL(F_ALL, false, false, nullptr);
+          else if (lean) RFX_LAUNCH_SMALL(0, true, false, w.image);
+          else RFX_LAUNCH_SMALL(F_ALL, true, false, w.image);
+        }
+#undef RFX_LAUNCH_SMALL
         return 1;
       }
       nThreads = (uint64_t)((fp.W + RFX_TILE_W - 1) / RFX_TILE_W) * ((rows + RFX_TILE_H - 1) / RFX_TILE_H) * 32;
