@@ -294,7 +294,8 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
     // (three-term dot products, the square, the product), while a ray that misses the sphere by m has disc = 4a(r^2 - m^2).  A
     // "noise hit" therefore needs m^2 - r^2 < 6e-7 |v|^2, i.e. m - r < min(3e-7 |v|^2 / r, 7.7e-4 |v|).  |v| is bounded by the
     // diagonal R of the box that holds every possible ray origin — the camera eye and all drop points (on spheres and
-    // triangles) — and every centre; each sphere's box is inflated by twice its own bound.  (Planes are unbounded: a drop point
+    // triangles) — and every centre; each sphere's box is inflated by twice its own bound, plus 1e-6 R for the device's slab
+    // test (fused arithmetic with clamped reciprocals: a box plane moves by at most 2^-22 |origin| along its axis).  (Planes are unbounded: a drop point
     // on a plane can lie outside the box; the reference's Scene cannot hold planes, and rfx_set_camera re-flattens the scene
     // when the eye leaves the box.)
     float lo[3] = { ctx->eye[0], ctx->eye[1], ctx->eye[2] }, hi[3] = { ctx->eye[0], ctx->eye[1], ctx->eye[2] };

@@ -164,8 +164,17 @@ __device__ __forceinline__ void intersectBlob(const BlobView & sc, int * __restr
   }
   else
   {
-    const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
-    const float lenD = sqrtf(a);
+    // Slab test.  The hierarchy only selects candidates for the exact test and its boxes carry margins (rfx_capi.cu), so — unlike
+    // everything the reference computes — this arithmetic may be fused: t = box * (1/d) - origin * (1/d) is one FFMA per plane
+    // instead of a subtraction and a multiplication.  Its error moves a box plane by at most 2^-22 |origin| along the axis, which
+    // the margins' 1e-6 * R term covers.  The reciprocals are clamped to +-1e30 so that an axis-parallel ray (1/0 = inf) gives
+    // large finite distances of the right sign instead of inf - inf.
+    const float ix = fminf(fmaxf(1.0f / d.x, -1e30f), 1e30f), iy = fminf(fmaxf(1.0f / d.y, -1e30f), 1e30f), iz = fminf(fmaxf(1.0f / d.z, -1e30f), 1e30f);
+    const float oxi = -(o.x * ix), oyi = -(o.y * iy), ozi = -(o.z * iz);
+    // a box whose entry lies beyond the closest hit so far cannot improve it: compared in ray-parameter space, with generous slack
+    // (0.1 % + 0.01 length units; +inf while there is no hit and in any-hit queries); refreshed after every leaf
+    const float invLen = 1.0f / sqrtf(a);
+    float reachT = (best.dist * 1.001f + 1e-2f) * invLen;
     // pair nodes: one trip tests both children of an inner node; the walk continues into a hit child in a register (the nearer
     // one) and only defers the other to the stack; "while-while": every lane walks to its next leaf, then the warp tests its
     // leaves together.  The bottom stack entry is the end marker.  (Single-box nodes, if-if order and far-child-first were
@@ -183,20 +192,18 @@ __device__ __forceinline__ void intersectBlob(const BlobView & sc, int * __restr
       {
         const float4 * q = pn + 4 * cur;
         const float4 n0 = SMEM ? q[0] : __ldg(q), n1 = SMEM ? q[1] : __ldg(q + 1), n2 = SMEM ? q[2] : __ldg(q + 2), n3 = SMEM ? q[3] : __ldg(q + 3);
-        const float ax1 = (n0.x - o.x) * ix, ax2 = (n1.x - o.x) * ix;
-        const float ay1 = (n0.y - o.y) * iy, ay2 = (n1.y - o.y) * iy;
-        const float az1 = (n0.z - o.z) * iz, az2 = (n1.z - o.z) * iz;
-        const float bx1 = (n2.x - o.x) * ix, bx2 = (n3.x - o.x) * ix;
-        const float by1 = (n2.y - o.y) * iy, by2 = (n3.y - o.y) * iy;
-        const float bz1 = (n2.z - o.z) * iz, bz2 = (n3.z - o.z) * iz;
+        const float ax1 = __fmaf_rn(n0.x, ix, oxi), ax2 = __fmaf_rn(n1.x, ix, oxi);
+        const float ay1 = __fmaf_rn(n0.y, iy, oyi), ay2 = __fmaf_rn(n1.y, iy, oyi);
+        const float az1 = __fmaf_rn(n0.z, iz, ozi), az2 = __fmaf_rn(n1.z, iz, ozi);
+        const float bx1 = __fmaf_rn(n2.x, ix, oxi), bx2 = __fmaf_rn(n3.x, ix, oxi);
+        const float by1 = __fmaf_rn(n2.y, iy, oyi), by2 = __fmaf_rn(n3.y, iy, oyi);
+        const float bz1 = __fmaf_rn(n2.z, iz, ozi), bz2 = __fmaf_rn(n3.z, iz, ozi);
         const float tminA = fmaxf(fmaxf(fminf(ax1, ax2), fminf(ay1, ay2)), fmaxf(fminf(az1, az2), 0.0f));
         const float tmaxA = fminf(fminf(fmaxf(ax1, ax2), fmaxf(ay1, ay2)), fmaxf(az1, az2));
         const float tminB = fmaxf(fmaxf(fminf(bx1, bx2), fminf(by1, by2)), fmaxf(fminf(bz1, bz2), 0.0f));
         const float tmaxB = fminf(fminf(fmaxf(bx1, bx2), fmaxf(by1, by2)), fmaxf(bz1, bz2));
-        // a box farther than the closest hit so far cannot improve it (generous slack; +inf while there is no hit / in any-hit queries)
-        const float reach = best.dist * 1.001f + 1e-2f;
-        const bool hitA = tminA <= tmaxA && !(tminA * lenD > reach);
-        const bool hitB = tminB <= tmaxB && !(tminB * lenD > reach);
+        const bool hitA = tminA <= tmaxA && !(tminA > reachT);
+        const bool hitB = tminB <= tmaxB && !(tminB > reachT);
         int ra = __float_as_int(n0.w), rb = __float_as_int(n1.w);
         if (hitA && hitB)
         {
@@ -210,6 +217,7 @@ __device__ __forceinline__ void intersectBlob(const BlobView & sc, int * __restr
       }
       if (cur == DONE) break;
       RFX_BLOB_LEAF(~cur)
+      reachT = (best.dist * 1.001f + 1e-2f) * invLen;
       cur = open ? stack[(--sp) * STRIDE] : DONE;
     }
   }
