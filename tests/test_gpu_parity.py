@@ -209,6 +209,48 @@ def test_blob_batch_kernel_equals_general_blob_kernel(capi, oracle, which, size,
     assert out[2][1] == rays
 
 
+@pytest.mark.parametrize("case", range(6))
+def test_wavefront_pair_randomized_against_tile_and_general_kernels(capi, case):
+    """The wavefront pair (k_blob_wave_first + k_blob_wave_rest) on seeded random scenes, sizes and depths — odd sizes, scenes in which
+    every path ends in its first segments (empty queue), a scene without a hierarchy (list walk), a sky-less box of mirrors in which no
+    path ends early (every pixel queued), depth exactly at the wavefront's threshold — for every number of tile segments: frames, ray
+    counts and stream positions identical to the single tile kernel and to the general kernel."""
+    rng = np.random.RandomState(100 + case)
+    W, H = int(rng.randint(33, 200)), int(rng.randint(9, 120))
+    depth = [4, 5, 7, 12, 20, 4][case]
+    if case == 1:      # nothing to hit: every path ends at the sky in its first segment
+        scene = {"ambient": ((0.9, 0.9, 1.0), 0.2), "skybox": S.synthetic_texture(64, 48, 2), "textures": [], "lights": [((5.0e9, 4.0e9, 3.0e9), 1.0e8, (1.0, 1.0, 1.0), 0.8)],
+                 "objects": [("sphere", (100.0 + k, 0.0, 0.0), 0.5, S.MT_METAL, (1.0, 1.0, 1.0), 1.0, 0.0) for k in range(40)]}
+    elif case == 3:    # closed box of perfect mirrors around the camera: no path ends before the depth limit
+        scene = {"ambient": ((1.0, 1.0, 1.0), 0.1), "skybox": None, "textures": [], "lights": [((0.0, 0.5, 0.0), 0.05, (1.0, 0.9, 0.8), 1.0)], "objects": []}
+        c = [(-9.0, -9.0, -9.0), (9.0, -9.0, -9.0), (9.0, 9.0, -9.0), (-9.0, 9.0, -9.0), (-9.0, -9.0, 9.0), (9.0, -9.0, 9.0), (9.0, 9.0, 9.0), (-9.0, 9.0, 9.0)]
+        for q in ((0, 1, 2, 3), (5, 4, 7, 6), (4, 0, 3, 7), (1, 5, 6, 2), (3, 2, 6, 7), (4, 5, 1, 0)):
+            for t in ((q[0], q[1], q[2]), (q[0], q[2], q[3]), (q[0], q[2], q[1]), (q[0], q[3], q[2])):     # both windings: one of them faces inward
+                scene["objects"].append(("tri", c[t[0]] + c[t[1]] + c[t[2]], S.MT_METAL, (1.0, 1.0, 1.0), 1.0, 0.0, -1, (0.0, 0.0, 0.0, 1.0, 1.0, 0.0)))
+        for k in range(40):
+            scene["objects"].append(("sphere", tuple(float(v) for v in rng.uniform(-6, 6, 3)), float(rng.uniform(0.3, 1.2)), S.MT_METAL, (1.0, 1.0, 1.0), 1.0, 0.0))
+    else:
+        scene = S.synthetic_scene(int(rng.randint(6, 14)), floor=S.synthetic_texture(64, 64, 3 + case), skybox=S.synthetic_texture(128, 96, 5))
+    cams = [S.default_camera(), S.orbit_cameras(11)[int(rng.randint(1, 10))]] if case != 3 else [S.camera_lookat((0.5, 0.2, -0.3), (3.0, 1.0, 2.0), 1.2)] * 2
+    out = {}
+    for key, path, wave, bvh in (("wave1", 2, 1, 1), ("wave2", 2, 2, 1), ("wave3", 2, 3, 1), ("wave2+L1", 2, 2, 1), ("wave2+list", 2, 2, 2), ("tile", 2, 0, 1), ("general", 3, 0, 1)):
+        c = capi.Context(0)
+        try:
+            c.load_scene(scene); c.set_seeds(1000 + case, 7); c.set_image_size(W, H)
+            c.force_path(path); c.set_bvh_mode(bvh); c.set_option("blob_wavefront", wave); c.set_option("blob_smem_bvh", 0 if key.endswith("L1") else 1)
+            c.stats_reset()
+            frames = c.render_frames(cams, depth)
+            st = c.stats()
+            if key.startswith("wave"):
+                assert st["launches_blob_fast"] == (2 * len(cams) if depth > wave else len(cams)), (key, st)
+            out[key] = (frames.copy(), st["rays"], st["bounces"], c.get_seeds())
+        finally:
+            c.close()
+    for key, got in out.items():
+        assert np.array_equal(got[0], out["general"][0]), (case, key)
+        assert got[1:] == out["general"][1:], (case, key)
+
+
 def test_blob_batch_kernel_float_image_equals_general_blob_kernel(capi):
     """Render API (float image) on a blob scene: whole frames and row-aligned chunks go to rfx_trace_blob.cu, ragged chunks to k_trace;
     the float images are bit-identical to k_trace rendering everything."""
