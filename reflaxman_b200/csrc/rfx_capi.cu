@@ -131,8 +131,9 @@ struct rfx_ctx
   SmallScene small; bool smallOk = false;   // constant-bank form of the same scene, when it fits
   // cost-ordered tile scheduling of the fast kernel (TileOrder, rfx_kernels.h): two list sets, used alternately
   uint32_t * dTileLists[2] = { nullptr, nullptr }; size_t tileListCap[2] = { 0, 0 };
-  uint32_t * dTileCounts = nullptr;         // [2][TILE_CLASSES]
-  int tileSlot = 0;                         // set the NEXT launch records into
+  uint32_t * dTileCounts = nullptr;         // [3][TILE_CLASSES]: recorded by the previous launch | recorded by this one | cleared by this one for the next
+  int tileSlot = 0;                         // list set the NEXT launch records into
+  int tileCountSlot = 0;                    // count set the NEXT launch records into (zero by then: cleared at creation or by the launch before)
   bool tileHistory = false;                 // the other set holds the order recorded by the previous launch ...
   uint64_t tileKey[4] = { 0, 0, 0, 0 };     // ... over this grid (image size, row range, strip split)
   bool tileOrdering = true;
@@ -516,17 +517,23 @@ int armTileOrder(rfx_ctx * ctx, TraceWork & w, cudaStream_t st)
                             ((uint64_t)w.fp.stripRows << 40) | ((uint64_t)w.fp.stripWorld << 20) | w.fp.stripRank };
   int rc;
   const int out = ctx->tileSlot, in = out ^ 1;
+  const int cOut = ctx->tileCountSlot, cIn = (cOut + 2) % 3, cNext = (cOut + 1) % 3;
   if ((rc = ensure(ctx, ctx->dTileLists[out], ctx->tileListCap[out], (size_t)grid * TILE_CLASSES)) != RFX_OK) return rc;
-  if (!ctx->dTileCounts) CK(cudaMalloc((void **)&ctx->dTileCounts, 2 * TILE_CLASSES * sizeof(uint32_t)));
-  CK(cudaMemsetAsync(ctx->dTileCounts + out * TILE_CLASSES, 0, TILE_CLASSES * sizeof(uint32_t), st));
+  if (!ctx->dTileCounts)
+  {
+    CK(cudaMalloc((void **)&ctx->dTileCounts, 3 * TILE_CLASSES * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(ctx->dTileCounts, 0, 3 * TILE_CLASSES * sizeof(uint32_t), st));
+  }
   w.order.outLists = ctx->dTileLists[out];
-  w.order.outCounts = ctx->dTileCounts + out * TILE_CLASSES;
+  w.order.outCounts = ctx->dTileCounts + cOut * TILE_CLASSES;
+  w.order.zeroCounts = ctx->dTileCounts + cNext * TILE_CLASSES;
   w.order.capacity = grid;
   if (ctx->tileHistory && memcmp(key, ctx->tileKey, sizeof(key)) == 0 && ctx->tileListCap[in] >= (size_t)grid * TILE_CLASSES)
   {
     w.order.inLists = ctx->dTileLists[in];
-    w.order.inCounts = ctx->dTileCounts + in * TILE_CLASSES;
+    w.order.inCounts = ctx->dTileCounts + cIn * TILE_CLASSES;
   }
+  ctx->tileCountSlot = cNext;
   memcpy(ctx->tileKey, key, sizeof(key));
   ctx->tileHistory = true;
   ctx->tileSlot = in;

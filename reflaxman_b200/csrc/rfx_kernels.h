@@ -61,7 +61,8 @@ struct TileOrder
   const uint32_t * inLists = nullptr;   // [TILE_CLASSES][capacity] packed (tileRow << 16 | tileColumnGroup); NULL = index order
   const uint32_t * inCounts = nullptr;  // [TILE_CLASSES], sums to the grid size
   uint32_t * outLists = nullptr;        // [TILE_CLASSES][capacity], NULL = do not record
-  uint32_t * outCounts = nullptr;       // [TILE_CLASSES], zeroed before the launch
+  uint32_t * outCounts = nullptr;       // [TILE_CLASSES], zero when the launch starts (the previous launch cleared it)
+  uint32_t * zeroCounts = nullptr;      // [TILE_CLASSES] the NEXT launch records into: this launch clears it (no memset between frames)
   uint32_t capacity = 0;
 };
 

@@ -473,6 +473,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
 {
   // which tile group does this CTA render: index order, or the previous launch's cost order (expensive classes first)
   uint32_t bx = blockIdx.x, by = blockIdx.y;
+  if (ord.zeroCounts && (blockIdx.x | blockIdx.y) == 0u && threadIdx.x < TILE_CLASSES) ord.zeroCounts[threadIdx.x] = 0u;   // for the next launch
   if (ord.inLists)
   {
     uint32_t total = 0;

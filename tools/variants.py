@@ -12,6 +12,8 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 VARIANTS = {
     # name: (defines, force_path)
     "base": ([], 1),
+    "mb9": (["RFX_SMALL_MINBLOCKS=9"], 1),      # 56 registers, 32 B of spills, 36 warps per SM
+    "mb10": (["RFX_SMALL_MINBLOCKS=10"], 1),    # 48 registers, 76 B of spills, 40 warps per SM
 }
 
 
