@@ -171,6 +171,7 @@ struct rfx_ctx
   uint32_t * dResolve = nullptr; size_t resolveCap = 0;   // K3 output of the Render-API read path (its own buffer and capacity)
   uint64_t maxCallsPerLaunch = 1ull << 25;    // bounds the ranked-state scratch (128 MB) for huge SSAA factors / 8K frames
   float bvhReach[6] = { 0, 0, 0, 0, 0, 0 };   // box of ray origins the hierarchy's margins were sized for (lo xyz, hi xyz)
+  float extraOrigins[6] = { FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX };   // box of the ray origins rfx_trace_rays was given
   // path queue of the blob scenes' wavefront kernel pair (rfx_trace_blob.cu): 64-byte records + {count, cursor}
   uint4 * dQueue = nullptr; size_t queueCap = 0;   // in uint4 units (4 per record)
   uint32_t * dQueueCtl = nullptr;
@@ -286,7 +287,10 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
   h.bvhFloat4 = 0;
   ctx->bvhDepth = 0;
   ctx->bvhFloat4 = 0;
-  const bool wantBvh = ctx->bvhMode == 1 ? !sph.empty() : ctx->bvhMode == 2 ? false : sph.size() > 32;
+  // automatic mode: more than 32 spheres, and no planes — a drop point on an (unbounded) plane can lie anywhere, so the box margins
+  // below, which are sized for ray origins inside a bounded region, could not be guaranteed (the reference's Scene cannot hold
+  // planes at all; mode 1 builds the hierarchy regardless, for tests)
+  const bool wantBvh = ctx->bvhMode == 1 ? !sph.empty() : ctx->bvhMode == 2 ? false : (sph.size() > 32 && pla.empty());
   if (wantBvh)
   {
     std::vector<BvhPrim> prims(sph.size());
@@ -300,6 +304,12 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
     // on a plane can lie outside the box; the reference's Scene cannot hold planes, and rfx_set_camera re-flattens the scene
     // when the eye leaves the box.)
     float lo[3] = { ctx->eye[0], ctx->eye[1], ctx->eye[2] }, hi[3] = { ctx->eye[0], ctx->eye[1], ctx->eye[2] };
+    for (int k = 0; k < 3; k++)
+      if (ctx->extraOrigins[k] <= ctx->extraOrigins[3 + k])   // origins of explicit ray lists (rfx_trace_rays)
+      {
+        lo[k] = std::min(lo[k], ctx->extraOrigins[k]);
+        hi[k] = std::max(hi[k], ctx->extraOrigins[3 + k]);
+      }
     for (size_t i = 0; i < sph.size(); i++)
       for (int k = 0; k < 3; k++)
       {
@@ -751,6 +761,7 @@ int rfx_scene_reset(rfx_ctx * ctx, const float ambient_rgb[3], float ambient_pow
   for (HostTex & t : ctx->tex) if (t.dev) cudaFree(t.dev);
   ctx->tex.clear(); ctx->objs.clear(); ctx->lights.clear();
   ctx->skyTex = -1;
+  for (int i = 0; i < 3; i++) { ctx->extraOrigins[i] = FLT_MAX; ctx->extraOrigins[3 + i] = -FLT_MAX; }
   for (int i = 0; i < 3; i++)
   {
     ctx->ambient[i] = ambient_rgb[i];
@@ -1225,6 +1236,27 @@ int rfx_trace_rays(rfx_ctx * ctx, int n, const float * origins, const float * ra
   int rc;
   if ((rc = useStream(ctx, st)) != RFX_OK) return rc;
   if ((rc = uploadScene(ctx, st)) != RFX_OK) return rc;
+  if (ctx->bvhDepth > 0)
+  {
+    // the hierarchy's box margins are sized for ray origins inside bvhReach: origins outside it widen the region and re-flatten
+    bool outside = false;
+    for (int i = 0; i < n; i++)
+      for (int k = 0; k < 3; k++)
+      {
+        const float v = origins[3 * (size_t)i + k];
+        if (!(v >= ctx->bvhReach[k] && v <= ctx->bvhReach[3 + k]) && v == v && fabsf(v) <= FLT_MAX)
+        {
+          outside = true;
+          ctx->extraOrigins[k] = std::min(ctx->extraOrigins[k], v);
+          ctx->extraOrigins[3 + k] = std::max(ctx->extraOrigins[3 + k], v);
+        }
+      }
+    if (outside)
+    {
+      ctx->sceneDirty = true;
+      if ((rc = uploadScene(ctx, st)) != RFX_OK) return rc;
+    }
+  }
   if ((rc = rankSamples(ctx, (uint64_t)n, false, st)) != RFX_OK) return rc;
   // ray buffers: origins | rays | rgb in one scratch allocation
   if ((rc = ensure(ctx, ctx->dRays, ctx->raysCap, (size_t)n * 9)) != RFX_OK) return rc;
@@ -1312,6 +1344,7 @@ int rfx_render_frames_device(rfx_ctx * ctx, int n_frames, const float * cams, in
     for (int f = f0; f < f0 + g; f++)
     {
       if ((rc = beginFrame(ctx, cams + 13 * (size_t)f, reflect_num, sample_num)) != RFX_OK) return rc;
+      if (ctx->sceneDirty && (rc = uploadScene(ctx, st)) != RFX_OK) return rc;   // this frame's eye left the box the BVH margins were sized for
       if ((rc = renderRange(ctx, 0, total, argb_device + (size_t)f * total, false, st,
                             pre ? ctx->dSampleStates + (size_t)(f - f0) * perFrame : nullptr)) != RFX_OK) return rc;
       ctx->cursor = total;
@@ -1354,6 +1387,7 @@ int rfx_render_frames(rfx_ctx * ctx, int n_frames, const float * cams, int refle
     if (pre && f % group == 0 && (rc = rankSamples(ctx, perFrame * std::min(group, n_frames - f), false, st)) != RFX_OK) return rc;
     if (f >= NS) CK(cudaStreamWaitEvent(st, ctx->evCopied[slot], 0));   // slot free again?
     if ((rc = beginFrame(ctx, cams + 13 * (size_t)f, reflect_num, sample_num)) != RFX_OK) return rc;
+    if (ctx->sceneDirty && (rc = uploadScene(ctx, st)) != RFX_OK) return rc;   // this frame's eye left the box the BVH margins were sized for
     if ((rc = renderRange(ctx, 0, total, ctx->dFrame[slot], false, st,
                           pre ? ctx->dSampleStates + (size_t)(f % group) * perFrame : nullptr)) != RFX_OK) return rc;
     ctx->cursor = total;
