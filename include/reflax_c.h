@@ -165,7 +165,9 @@ RFX_API int rfx_enable_profiling(rfx_ctx * ctx, int on);
  * rfx_render_frames alternates between (1 or 2, default 1).  "blob_wavefront": scenes that do not fit the constant bank render
  * their one-sample ARGB frames of reflection depth >= 4 with a two-kernel wavefront — the first k segments of every path in pixel
  * tiles, the rest from a path queue (k = the value, default 2; 0 = the single tile kernel).  "blob_smem_bvh": the queue-driven
- * kernel keeps a small sphere hierarchy in shared memory (default 1).  Frames are bit-identical under every setting. */
+ * kernel keeps a small sphere hierarchy in shared memory (default 1).  "tile_order_period": the cost-ordered tile scheduling of the
+ * constant-bank fast kernel records the tiles' cost classes on every k-th launch over the same grid and replays the last recording
+ * in between (default 8).  Frames are bit-identical under every setting. */
 RFX_API int rfx_set_option(rfx_ctx * ctx, const char * name, int64_t value);
 /* kernel selection: 0 = automatic (constant-bank kernel when the scene fits, the general blob kernel otherwise),
  * 1 = constant-bank kernel if it fits, 2 = always the blob kernels (tile / wavefront kernels for row-aligned slices, the general

@@ -134,6 +134,9 @@ struct rfx_ctx
   uint32_t * dTileCounts = nullptr;         // [3][TILE_CLASSES]: recorded by the previous launch | recorded by this one | cleared by this one for the next
   int tileSlot = 0;                         // list set the NEXT launch records into
   int tileCountSlot = 0;                    // count set the NEXT launch records into (zero by then: cleared at creation or by the launch before)
+  int tileRecordPeriod = 8;                 // rfx_set_option "tile_order_period": the cost classes are recorded on every k-th launch over a grid; the
+                                            // launches in between replay the last recording (no CTA barrier, no atomic at their end: -2 % kernel time)
+  int tileReuse = 0;                        // launches that reused the last recording
   bool tileHistory = false;                 // the other set holds the order recorded by the previous launch ...
   uint64_t tileKey[4] = { 0, 0, 0, 0 };     // ... over this grid (image size, row range, strip split)
   bool tileOrdering = true;
@@ -528,6 +531,17 @@ int armTileOrder(rfx_ctx * ctx, TraceWork & w, cudaStream_t st)
   int rc;
   const int out = ctx->tileSlot, in = out ^ 1;
   const int cOut = ctx->tileCountSlot, cIn = (cOut + 2) % 3, cNext = (cOut + 1) % 3;
+  if (ctx->tileRecordPeriod > 1 && ctx->tileHistory && memcmp(key, ctx->tileKey, sizeof(key)) == 0 && ctx->tileReuse + 1 < ctx->tileRecordPeriod &&
+      ctx->tileListCap[in] >= (size_t)grid * TILE_CLASSES)
+  {
+    // replay the last recording without recording again (the kernel then has no CTA barrier and no atomic at its end)
+    w.order.inLists = ctx->dTileLists[in];
+    w.order.inCounts = ctx->dTileCounts + cIn * TILE_CLASSES;
+    w.order.capacity = grid;
+    ctx->tileReuse++;
+    return RFX_OK;
+  }
+  ctx->tileReuse = 0;
   if ((rc = ensure(ctx, ctx->dTileLists[out], ctx->tileListCap[out], (size_t)grid * TILE_CLASSES)) != RFX_OK) return rc;
   if (!ctx->dTileCounts)
   {
@@ -1484,6 +1498,12 @@ int rfx_set_option(rfx_ctx * ctx, const char * name, int64_t value)
   {
     if (value < 0 || value > 64) return fail(ctx, RFX_ERR_ARG, "rfx_set_option: blob_wavefront must be 0 (off) or the number of first segments (1..64)");
     ctx->blobWavefront = (int)value;
+    return RFX_OK;
+  }
+  if (!strcmp(name, "tile_order_period"))
+  {
+    if (value < 1) return fail(ctx, RFX_ERR_ARG, "rfx_set_option: tile_order_period must be >= 1");
+    ctx->tileRecordPeriod = (int)std::min<int64_t>(value, 1 << 30);
     return RFX_OK;
   }
   if (!strcmp(name, "blob_smem_bvh"))

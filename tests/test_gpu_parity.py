@@ -390,26 +390,30 @@ def test_fast_kernel_equals_general_kernel_full_size(capi):
 
 def test_tile_ordering_does_not_change_results(capi):
     """Cost-ordered tile scheduling only permutes which CTA renders which tile group: frames rendered with the history of the
-    previous launch, without it, and across an image-size change (history dropped) are bit-identical."""
-    cams = S.orbit_cameras(9)[:4]
+    previous launch (recorded on every launch, on every 2nd, on every 8th — the launches in between replay the last recording),
+    without it, and across an image-size change (history dropped) are bit-identical."""
+    cams = S.orbit_cameras(9)[:6]
     frames = {}
-    for on in (True, False):
+    for key, on, period in (("every", True, 1), ("every2nd", True, 2), ("default", True, None), ("off", False, None)):
         c = capi.Context(0)
         try:
             c.load_scene(S.default_scene()); c.set_seeds(77, 77)
             c.set_tile_ordering(on)
+            if period:
+                c.set_option("tile_order_period", period)
             c.set_image_size(200, 120)
-            a = c.render_frames(cams, 20)            # frame 0 in index order, frames 1-3 in the order frame k-1 recorded
+            a = c.render_frames(cams, 20)            # frame 0 in index order, the others in a recorded order
             c.set_image_size(136, 96)                # different grid: the history must not be reused
             b = c.render_frames(cams[:2], 20)
             c.set_image_size(200, 120)
             d = c.render_frames(cams[:1], 20)
-            frames[on] = (a, b, d, c.stats()["rays"])
+            frames[key] = (a, b, d, c.stats()["rays"])
         finally:
             c.close()
-    for x, y in zip(frames[True][:3], frames[False][:3]):
-        assert np.array_equal(x, y)
-    assert frames[True][3] == frames[False][3]
+    for key in ("every", "every2nd", "default"):
+        for x, y in zip(frames[key][:3], frames["off"][:3]):
+            assert np.array_equal(x, y), key
+        assert frames[key][3] == frames["off"][3], key
 
 
 def _lcg_state_at(position):

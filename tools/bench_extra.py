@@ -147,6 +147,8 @@ def config5(env, steps=3, warmup=3):
     Wd, Hd, depth, NF = 1920, 1080, 20, 240
     ctx = capi.Context(env.local)
     ctx.load_scene(S.default_scene()); ctx.set_image_size(Wd, Hd)
+    if os.environ.get("RFX_TILE_ORDER_PERIOD"):
+        ctx.set_option("tile_order_period", int(os.environ["RFX_TILE_ORDER_PERIOD"]))   # A/B knob (default 8)
     cams = S.orbit_cameras(NF)
     mine = P.frame_shard(NF, env.world, env.rank)
     packed = capi.pack_cameras([cams[f] for f in mine])
