@@ -106,6 +106,11 @@ RFX_API int rfx_get_seeds(rfx_ctx * ctx, uint32_t out[2]);            /* current
 /* advance the randDir stream as if n Scene::trace calls had run (frame sharding).  The stream's accept pattern is tabulated
  * over the LCG's whole 2^32-state cycle at rfx_create, so the cost does not depend on n: one small kernel. */
 RFX_API int rfx_skip_samples(rfx_ctx * ctx, uint64_t n_trace_calls);
+/* diagnostic: the library decides whether a draw-triple of Vector3::randomInsideSphere is accepted (Vector3.cpp:185) with an integer
+ * test and falls back to the reference's float expression inside a guard band; this runs both on every triple of the LCG's whole
+ * 2^32-state cycle.  out[0] = triples on which they disagree (0 = the decisions are the reference's, by exhaustion),
+ * out[1] = triples inside the guard band.  About 20 ms. */
+RFX_API int rfx_selftest_rng(rfx_ctx * ctx, uint64_t out[2]);
 
 /* ---- Render (reference Render.h:30-41) ----------------------------------------------------------------- */
 RFX_API int rfx_set_image_size(rfx_ctx * ctx, uint32_t width, uint32_t height);   /* Render::setImageSize, Render.cpp:57-80 */

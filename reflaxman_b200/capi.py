@@ -51,6 +51,7 @@ SYMBOLS = [
     ("rfx_set_seeds", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     ("rfx_get_seeds", C.c_int, [C.c_void_p, _u32p]),
     ("rfx_skip_samples", C.c_int, [C.c_void_p, C.c_uint64]),
+    ("rfx_selftest_rng", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     ("rfx_set_image_size", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     ("rfx_render_begin", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("rfx_render_next", C.c_int, [C.c_void_p, C.c_uint32]),
@@ -195,6 +196,13 @@ class Context:
     def get_seeds(self):
         out = (C.c_uint32 * 2)()
         self._ck(self.L.rfx_get_seeds(self.h, out), "rfx_get_seeds")
+        return int(out[0]), int(out[1])
+
+    def selftest_rng(self):
+        """(triples of the whole LCG cycle on which K1's integer accept test and the reference's float expression disagree,
+        triples inside the guard band)"""
+        out = (C.c_uint64 * 2)()
+        self._ck(self.L.rfx_selftest_rng(self.h, out), "rfx_selftest_rng")
         return int(out[0]), int(out[1])
 
     def skip_samples(self, n):

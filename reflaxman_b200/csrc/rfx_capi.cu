@@ -924,6 +924,22 @@ int rfx_get_seeds(rfx_ctx * ctx, uint32_t out[2])
   return checkStatus(ctx);
 }
 
+int rfx_selftest_rng(rfx_ctx * ctx, uint64_t out[2])
+{
+  if (!ctx || !out) return RFX_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  unsigned long long * d = nullptr;
+  CK(cudaMalloc((void **)&d, 2 * sizeof(unsigned long long)));
+  cudaError_t e = cudaMemset(d, 0, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) { ctx->stats.kernel_launches += launchRngSelftest(d, ctx->stream); e = cudaStreamSynchronize(ctx->stream); }
+  unsigned long long h[2] = { 0, 0 };
+  if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, RFX_ERR_CUDA, std::string("rfx_selftest_rng: ") + cudaGetErrorString(e));
+  out[0] = h[0]; out[1] = h[1];
+  return RFX_OK;
+}
+
 int rfx_skip_samples(rfx_ctx * ctx, uint64_t n)
 {
   if (!ctx) return RFX_ERR_ARG;

@@ -56,12 +56,40 @@ __device__ __forceinline__ float lcgDrawUnit(uint32_t & s)
   return divExact(float(r), 16383.5f, RFX_RCP_16383_5) - 1.f;
 }
 
+// Accept test of one draw-triple WITHOUT producing the direction (K1 only needs the decision): advances s by three draws.
+// With r the 15-bit draw, the reference's component is x = r / 16383.5 - 1 = (2r - 32767) / 32767 exactly in the reals, so
+// x^2 + y^2 + z^2 <= 1 is S <= 32767^2 for the integer S = sum (2r - 32767)^2 (< 2^32).  The reference decides on the FLOAT
+// evaluation, whose result differs from the real value by at most 1.2e-6 near 1 (correctly rounded division: 1.2e-7 on x; each
+// square 3e-7; two additions 2.4e-7) = 1 300 in units of S.  Outside a guard band of 8 192 around 32767^2 the integer test
+// therefore gives the reference's decision; inside it (3 triples in a million) the float expression is evaluated as the
+// reference does.  rfx_selftest_rng compares the two over every triple of the LCG's whole cycle.
+__device__ __forceinline__ bool rngAcceptFloat(int a, int b, int c);
+__device__ __forceinline__ bool rngAccept(uint32_t & s)
+{
+  s = 214013u * s + 2531011u; const int a = (int)((s >> 16) & 0x7FFFu);
+  s = 214013u * s + 2531011u; const int b = (int)((s >> 16) & 0x7FFFu);
+  s = 214013u * s + 2531011u; const int c = (int)((s >> 16) & 0x7FFFu);
+  const int da = 2 * a - 32767, db = 2 * b - 32767, dc = 2 * c - 32767;
+  const uint32_t S = (uint32_t)(da * da) + (uint32_t)(db * db) + (uint32_t)(dc * dc);
+  const uint32_t R2 = 32767u * 32767u, GUARD = 8192u;
+  if (S < R2 - GUARD) return true;
+  if (S > R2 + GUARD) return false;
+  return rngAcceptFloat(a, b, c);
+}
+
 // one draw-triple: advances s by three draws; true when the candidate lies inside the unit sphere (Vector3.cpp:185)
 __device__ __forceinline__ bool rngTriple(uint32_t & s, float & x, float & y, float & z)
 {
   x = lcgDrawUnit(s);
   y = lcgDrawUnit(s);
   z = lcgDrawUnit(s);
+  return !((x * x + y * y) + z * z > 1.f);
+}
+
+__device__ __forceinline__ bool rngAcceptFloat(int a, int b, int c)   // the reference's own expression, Vector3.cpp:182-185
+{
+  const float x = divExact(float(a), 16383.5f, RFX_RCP_16383_5) - 1.f, y = divExact(float(b), 16383.5f, RFX_RCP_16383_5) - 1.f,
+              z = divExact(float(c), 16383.5f, RFX_RCP_16383_5) - 1.f;
   return !((x * x + y * y) + z * z > 1.f);
 }
 

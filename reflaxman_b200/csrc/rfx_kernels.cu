@@ -93,10 +93,7 @@ __device__ __forceinline__ uint32_t rngThreadMask(uint32_t sStart, uint32_t r, u
   uint32_t s = sStart, mask = 0;
 #pragma unroll
   for (int k = 0; k < RNG_TRIPLES_PER_THREAD; k++)
-  {
-    float x, y, z;
-    if (rngTriple(s, x, y, z)) mask |= 1u << k;
-  }
+    if (rngAccept(s)) mask |= 1u << k;
   const uint32_t qFirst = j * RNG_TRIPLES_PER_BLOCK + threadIdx.x * RNG_TRIPLES_PER_THREAD, nr = rngClassTriples(r);
   if (qFirst + RNG_TRIPLES_PER_THREAD > nr) mask &= qFirst >= nr ? 0u : ((1u << (nr - qFirst)) - 1u);
   return mask;
@@ -134,6 +131,44 @@ __global__ void __launch_bounds__(RNG_THREADS) k_rng_table(uint32_t * __restrict
   int total;
   rngBlockScan(__popc(mask), total);
   if (threadIdx.x == 0) counts[r * RNG_CLASS_BLOCKS + j] = (uint32_t)total;
+}
+
+// Self-test: the integer accept test with its guard band (rngAccept) against the reference's float expression (rngTriple) on
+// EVERY triple of the LCG's cycle — all three residue classes of start positions, 4.3e9 triples: proof by exhaustion that K1's
+// decisions are the reference's.  out[0] = triples whose decisions differ (must be 0), out[1] = triples inside the guard band.
+__global__ void __launch_bounds__(RNG_THREADS) k_rng_selftest(unsigned long long * __restrict__ out)
+{
+  const uint32_t r = blockIdx.y, j = blockIdx.x;
+  uint32_t s1 = rngThreadStart(r, j), s2 = s1;
+  uint32_t differ = 0, band = 0;
+#pragma unroll
+  for (int k = 0; k < RNG_TRIPLES_PER_THREAD; k++)
+  {
+    uint32_t t = s2;
+    t = 214013u * t + 2531011u; const int a = (int)((t >> 16) & 0x7FFFu);
+    t = 214013u * t + 2531011u; const int b = (int)((t >> 16) & 0x7FFFu);
+    t = 214013u * t + 2531011u; const int c = (int)((t >> 16) & 0x7FFFu);
+    const int da = 2 * a - 32767, db = 2 * b - 32767, dc = 2 * c - 32767;
+    const uint32_t S = (uint32_t)(da * da) + (uint32_t)(db * db) + (uint32_t)(dc * dc), R2 = 32767u * 32767u;
+    band += (S >= R2 - 8192u && S <= R2 + 8192u) ? 1u : 0u;
+    float x, y, z;
+    const bool viaFloat = rngTriple(s2, x, y, z);
+    const bool viaInt = rngAccept(s1);
+    differ += (viaFloat != viaInt || s1 != s2) ? 1u : 0u;
+  }
+  differ = __reduce_add_sync(0xffffffffu, differ);
+  band = __reduce_add_sync(0xffffffffu, band);
+  if ((threadIdx.x & 31u) == 0u)
+  {
+    if (differ) atomicAdd(&out[0], (unsigned long long)differ);
+    if (band) atomicAdd(&out[1], (unsigned long long)band);
+  }
+}
+
+int launchRngSelftest(unsigned long long * out, cudaStream_t st)
+{
+  k_rng_selftest<<<dim3(RNG_CLASS_BLOCKS, 3), RNG_THREADS, 0, st>>>(out);
+  return 1;
 }
 
 // one CTA per class: prefix[r][j] = accepted triples of class r in blocks < j, j = 0 .. RNG_CLASS_BLOCKS (the last entry is the class total)

@@ -44,6 +44,9 @@ struct RngWork
 int initRngTables();
 // fills the cycle's accept-count table: counts [3][RNG_CLASS_BLOCKS] scratch, prefix [3][RNG_CLASS_BLOCKS + 1]; returns kernels launched
 int launchRngTable(uint32_t * counts, uint32_t * prefix, cudaStream_t st);
+// K1 self-test over the LCG's whole cycle: out[0] = triples on which the integer accept test and the reference's float expression
+// disagree (must be 0), out[1] = triples inside the guard band (decided by the float expression); out must be zeroed
+int launchRngSelftest(unsigned long long * out, cudaStream_t st);
 // number of blocks that over-provisions n accepted triples (acceptance pi/6 = 0.5236)
 uint32_t rngBlocksFor(uint64_t n);
 // enqueue locate (+ rank); returns the number of kernels launched

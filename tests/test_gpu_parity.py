@@ -455,6 +455,18 @@ def test_random_stream_across_the_lcg_cycle_wrap(capi, oracle, back):
         c.close(); d.close()
 
 
+def test_k1_accept_test_equals_reference_expression_on_the_whole_lcg_cycle(capi):
+    """K1 decides acceptance of a draw-triple with an integer test and evaluates the reference's float expression only inside a guard
+    band around the unit sphere's surface; rfx_selftest_rng runs both on all 4.29e9 triples of the LCG's cycle: no disagreement."""
+    c = capi.Context(0)
+    try:
+        differ, band = c.selftest_rng()
+        assert differ == 0, "%d triples decided differently from the reference's float expression" % differ
+        assert 1000 < band < 1_000_000, band         # the band exists and is thin (~3e-6 of the triples)
+    finally:
+        c.close()
+
+
 def test_stream_skip_matches_serial_stream(capi, oracle):
     """rfx_skip_samples finds the end of the skipped stretch in the table of the LCG cycle (one small kernel whatever n is):
     the resulting stream state equals the oracle's serial walk, skips compose, and a skip longer than a whole residue class
