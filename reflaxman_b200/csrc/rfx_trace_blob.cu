@@ -1,23 +1,25 @@
-// rfx_trace_blob.cu — K2 for scenes that do not fit the constant bank (config 4: 1024 spheres): row-aligned slices, ARGB and/or
-// float image out; one sample per pixel (the batch path the bench times) or grid SSAA / additive jitter (Render API, MULTI).
-// Block preview, ragged slices and signature runs of such scenes stay on k_trace (rfx_kernels.cu), whose results this kernel
-// reproduces bit for bit (tests/test_gpu_parity.py::test_blob_batch_kernel_*).
+// rfx_trace_blob.cu — K2 for scenes that do not fit the constant bank (config 4: 1024 spheres), every mode of Render::renderNext:
+//   k_trace_blob<MULTI>                    row-aligned slices, ARGB and/or float image; one sample per pixel or grid SSAA / additive jitter
+//   k_blob_wave_first + k_blob_wave_rest   one-sample ARGB frames of reflection depth >= 4 as a two-kernel wavefront (below)
+//   k_trace_blob_any                       arbitrary pixel slices, block preview, signature runs
+//   k_trace_blob_rays                      Scene::trace for an explicit ray list (rfx_trace_rays)
+// All of them run ONE restatement of Scene::trace, traceBlob<SIG, MODE> (round 1 kept a second one, k_trace in rfx_kernels.cu, with two
+// inlined traversals; it is gone).
 //
 // It is the structure of the constant-bank kernel (rfx_trace_small.cu) applied to the scene blob in global memory:
 //   * Scene::trace as a per-lane state machine with ONE traversal site: the query in flight is the bounce segment (closest
-//     hit) or the shadow ray of light li (any hit).  k_trace inlines the traversal twice and weighs 111 KB of SASS — a fifth
-//     of its stall cycles wait for instructions; this kernel is 2 600 instructions.
-//   * The BVH over the spheres (built by rfx_capi.cu, boxes inflated far beyond the float error of the exact test) only
+//     hit) or the shadow ray of light li (any hit).
+//   * The BVH over the spheres (built by rfx_capi.cu, every box inflated beyond the rounding noise of the exact test) only
 //     selects which spheres get the reference's exact test.  It is walked over PAIR NODES (both children's boxes in the parent,
 //     four 16-byte loads per trip): the walk continues into the nearer hit child in a register and defers the other one to a
 //     stack in shared memory (one column per thread); "while-while" order — every lane walks to its next leaf, then the warp
 //     tests its leaves together.  A leaf is four contiguous sphere records (NaN-padded) tested behind one gate, like a quad of
-//     the constant-bank kernel.
+//     the constant-bank kernel.  The slab test is the one piece of arithmetic here that is not the reference's, so it is fused.
 //   * 4x8 pixel tiles per warp on a 2-D grid, 128-bit framebuffer stores, 64 registers / 8 CTAs per SM.
-// Each step was measured (profiles/README.md: 6.66 -> 4.68 ms for a 3840x2160 frame of the 1024-sphere scene at depth 8).
+// Each step was measured (profiles/README.md: 6.66 -> 3.80 ms for a 3840x2160 frame of the 1024-sphere scene at depth 8).
 //
-// ARITHMETIC CONTRACT: as in rfx_trace_small.cu — --fmad=false, every + - * / sqrtf is the IEEE binary32 RN operation in the
-// reference's evaluation order; the expressions below are the ones of rfx_trace_small.cu / rfx_kernels.cu.
+// ARITHMETIC CONTRACT: as in rfx_trace_small.cu — --fmad=false, every + - * / sqrtf of the reference's arithmetic is the IEEE
+// binary32 RN operation in the reference's evaluation order; the expressions below are the ones of rfx_trace_small.cu.
 // Reference map (path:line under /root/reference/src/common): Sphere.cpp:44-85, Triangle.cpp:53-108, Plane.cpp:36-73,
 // Scene.cpp:73-236, Render.cpp:136-215.
 #include "rfx_kernels.h"
