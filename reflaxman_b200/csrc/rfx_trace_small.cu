@@ -474,7 +474,15 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
   // which tile group does this CTA render: index order, or the previous launch's cost order (expensive classes first)
   uint32_t bx = blockIdx.x, by = blockIdx.y;
   if (ord.zeroCounts && (blockIdx.x | blockIdx.y) == 0u && threadIdx.x < TILE_CLASSES) ord.zeroCounts[threadIdx.x] = 0u;   // for the next launch
-  if (ord.inLists)
+  if (!ord.inLists)
+  {
+    // no recording to replay (first launch over this grid): start the tile rows of the middle of the slice first and work outwards.
+    // The subject of a picture tends to sit near its centre and the long paths with it; in plain index order they would start
+    // in the middle of the launch and the last rows of sky would run against a long tail.
+    const uint32_t mid = gridDim.y >> 1, b = blockIdx.y;
+    by = (b & 1u) ? mid - 1u - (b >> 1) : mid + (b >> 1);      // even indices walk up from the middle row, odd ones down: a permutation
+  }
+  else
   {
     uint32_t total = 0;
 #pragma unroll
