@@ -130,7 +130,8 @@ RFX_API int rfx_enable_signatures(rfx_ctx * ctx, int on);
  * rfx_render_begin.  Ranges must be issued in increasing order; the random streams are advanced over the pixels in between,
  * so every range consumes exactly the draws it would get in a full-frame render, and rfx_render_finish advances them to the
  * end of the frame.  argb_device (optional) is a FULL-FRAME ARGB buffer; it may live on another GPU (peer mapping over
- * NVLink, see rfx_ipc_*): the kernel then stores its pixels straight into the gathering GPU's framebuffer. */
+ * NVLink, see rfx_ipc_*): the kernel then stores its pixels straight into the gathering GPU's framebuffer.  Any 4-byte aligned
+ * frame is accepted (16-byte aligned frames of a width that is a multiple of 4 take the kernels with 128-bit stores). */
 RFX_API int rfx_render_range(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argb_device, void * stream);
 RFX_API int rfx_render_finish(rfx_ctx * ctx);
 /* the same for the usual partition — interleaved strips of strip_rows rows, strip s owned by rank s % world — in ONE random-stream
@@ -174,15 +175,17 @@ RFX_API int rfx_enable_profiling(rfx_ctx * ctx, int on);
  * constant-bank fast kernel records the tiles' cost classes on every k-th launch over the same grid and replays the last recording
  * in between (default 8).  Frames are bit-identical under every setting. */
 RFX_API int rfx_set_option(rfx_ctx * ctx, const char * name, int64_t value);
-/* kernel selection: 0 = automatic (constant-bank kernel when the scene fits, the general blob kernel otherwise),
+/* kernel selection: 0 = automatic (constant-bank kernels when the scene fits, the blob kernels otherwise),
  * 1 = constant-bank kernel if it fits, 2 = always the blob kernels (tile / wavefront kernels for row-aligned slices, the general
  * one otherwise), 3 = always the general blob kernel.  Results are identical; tests use it. */
 RFX_API int rfx_force_path(rfx_ctx * ctx, int path);
-/* acceleration structure of the general blob kernel: 0 = automatic (bounding-volume hierarchy over the spheres when there are
- * more than 32), 1 = always, 2 = never (the reference's brute-force list walk).  Results are identical; tests compare them. */
+/* acceleration structure of the blob kernels: 0 = automatic (bounding-volume hierarchy over the spheres when there are more than
+ * 32 and the scene holds no unbounded plane), 1 = always, 2 = never (the reference's brute-force list walk).  Results are
+ * identical; tests compare them. */
 RFX_API int rfx_set_bvh_mode(rfx_ctx * ctx, int mode);
-/* cost-ordered tile scheduling of the constant-bank fast kernel: every launch records which tiles held long paths and the next
- * launch over the same image starts those first (1 = on, the default; 0 = always index order).  Results are identical. */
+/* cost-ordered tile scheduling of the constant-bank fast kernel: launches record which tiles held long paths (every
+ * "tile_order_period"-th launch over a grid) and the following launches over the same grid start those first (1 = on, the
+ * default; 0 = off: middle rows of the slice first, outwards).  Results are identical. */
 RFX_API int rfx_set_tile_ordering(rfx_ctx * ctx, int on);
 
 #ifdef __cplusplus
