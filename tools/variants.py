@@ -12,8 +12,9 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 VARIANTS = {
     # name: (defines, force_path)
     "base": ([], 1),
-    "mb9": (["RFX_SMALL_MINBLOCKS=9"], 1),      # 56 registers, 32 B of spills, 36 warps per SM
-    "mb10": (["RFX_SMALL_MINBLOCKS=10"], 1),    # 48 registers, 76 B of spills, 40 warps per SM
+    "t64": (["RFX_SMALL_THREADS=64", "RFX_SMALL_MINBLOCKS=16"], 1),     # 2-warp CTAs: slots free up per pair of tiles
+    "t32": (["RFX_SMALL_THREADS=32", "RFX_SMALL_MINBLOCKS=32"], 1),     # 1-warp CTAs
+    "t256": (["RFX_SMALL_THREADS=256", "RFX_SMALL_MINBLOCKS=4"], 1),
 }
 
 
