@@ -165,6 +165,7 @@ struct rfx_ctx
   uint32_t * dRngPrefix = nullptr;            // [3][RNG_CLASS_BLOCKS + 1] accept-count prefix sums of the LCG cycle (built at creation)
   RngLocate * dRngLocate = nullptr;
   uint32_t * dSampleStates = nullptr; size_t statesCap = 0;
+  uint32_t * dOwnBlocks = nullptr; size_t ownBlocksCap = 0;   // split frames: K1's list of the blocks that hold this GPU's ranks
   int * dStatus = nullptr;
   float * dRays = nullptr; size_t raysCap = 0;   // rfx_trace_rays scratch
 
@@ -513,6 +514,12 @@ int rankSamples(rfx_ctx * ctx, uint64_t n, bool skipOnly, cudaStream_t st, uint6
   w.n = n;
   w.nBlocks = nBlocks;
   w.ownPeriod = ownPeriod; w.ownWorld = ownWorld; w.ownRank = ownRank;
+  if (ownWorld && !skipOnly)
+  {
+    const uint32_t bound = rngOwnBlocksBound(n, ownPeriod, ownWorld, nBlocks);
+    if ((rc = ensure(ctx, ctx->dOwnBlocks, ctx->ownBlocksCap, bound)) != RFX_OK) return rc;
+    w.ownList = ctx->dOwnBlocks; w.ownListCap = (uint32_t)std::min<size_t>(ctx->ownBlocksCap, 0xFFFFFFFFu);
+  }
   ctx->stats.kernel_launches += launchRngRank(w, st);
   CK(cudaGetLastError());
   ctx->rngSlot ^= 1;
@@ -737,7 +744,7 @@ void rfx_destroy(rfx_ctx * ctx)
   cudaFree(ctx->dRngPrefix); cudaFree(ctx->dRngLocate); cudaFree(ctx->dSampleStates); cudaFree(ctx->dStatus);
   cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dBvhNodes); cudaFree(ctx->dBvhPrims); cudaFree(ctx->dTileLists[0]); cudaFree(ctx->dTileLists[1]); cudaFree(ctx->dTileCounts);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
-  cudaFree(ctx->dResolve); cudaFree(ctx->dQueue); cudaFree(ctx->dQueueCtl);
+  cudaFree(ctx->dResolve); cudaFree(ctx->dQueue); cudaFree(ctx->dQueueCtl); cudaFree(ctx->dOwnBlocks);
   for (int i = 0; i < rfx_ctx::FRAME_SLOTS; i++)
   {
     cudaFree(ctx->dFrame[i]);

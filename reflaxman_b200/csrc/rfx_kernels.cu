@@ -16,6 +16,7 @@
 #include "rfx_device.cuh"
 #include <float.h>
 #include <math.h>
+#include <algorithm>
 
 namespace rfx
 {
@@ -213,6 +214,37 @@ __global__ void __launch_bounds__(1024) k_rng_prefix(const uint32_t * __restrict
   if (threadIdx.x == 0) prefix[RNG_CLASS_BLOCKS] = carryS;
 }
 
+// virtual block v of a pass -> block j of class r, and the ranks [first, next) of the stream that start in it
+struct RngBlock { uint32_t r, j; long long first, next; bool valid; };
+__device__ __forceinline__ RngBlock rngVirtualBlock(uint32_t v, uint32_t r0, uint32_t j0, uint32_t r1, uint32_t nb1, unsigned long long off1,
+                                                    unsigned long long seg1, const uint32_t * __restrict__ prefix)
+{
+  RngBlock b;
+  long long off;
+  if (v < nb1) { b.r = r0; b.j = j0 + v; off = (long long)off1; }
+  else         { b.r = r1; b.j = v - nb1; off = -(long long)seg1; }
+  b.valid = b.j < RNG_CLASS_BLOCKS;
+  b.first = 0; b.next = 0;
+  if (b.valid)
+  {
+    const uint32_t * pre = prefix + b.r * (RNG_CLASS_BLOCKS + 1);
+    b.first = (long long)pre[b.j] - off; b.next = (long long)pre[b.j + 1] - off;
+  }
+  return b;
+}
+
+// split frames: ranks are dealt to the GPUs in strips of ownPeriod ranks, strip s to GPU s % ownWorld.  Does a block whose ranks are
+// [first, next) (clipped to [0, n)) hold a rank of ownRank's — or rank n-1, whose block writes the stream-end state?
+__device__ __forceinline__ bool rngBlockOwned(long long first, long long next, unsigned long long n, unsigned long long ownPeriod, uint32_t ownWorld, uint32_t ownRank)
+{
+  const unsigned long long lo = (unsigned long long)(first < 0 ? 0 : first), hi = (unsigned long long)(next > (long long)n ? (long long)n : next) - 1ull;
+  if (hi >= n - 1) return true;
+  const unsigned long long s0 = lo / ownPeriod, s1 = hi / ownPeriod;
+  if (s1 - s0 + 1 >= ownWorld) return true;
+  const uint32_t ahead = (ownRank + ownWorld - (uint32_t)(s0 % ownWorld)) % ownWorld;   // strips from s0 to the next one ownRank owns
+  return (unsigned long long)ahead <= s1 - s0;
+}
+
 __global__ void __launch_bounds__(RNG_THREADS) k_rng_locate(const uint32_t * __restrict__ stateIn, const uint32_t * __restrict__ prefix,
                                                             unsigned long long n, RngLocate * __restrict__ loc,
                                                             uint32_t * __restrict__ stateOut /* skip-only pass: where the stream ends; else NULL */,
@@ -245,6 +277,7 @@ __global__ void __launch_bounds__(RNG_THREADS) k_rng_locate(const uint32_t * __r
   if (threadIdx.x == 0)
   {
     loc->r0 = r0; loc->j0 = j0; loc->r1 = r1; loc->nb1 = RNG_CLASS_BLOCKS - j0; loc->off1 = off1; loc->seg1 = seg1;
+    loc->ownCount = 0;
   }
   if (!stateOut) return;
 
@@ -285,35 +318,64 @@ __global__ void __launch_bounds__(RNG_THREADS) k_rng_locate(const uint32_t * __r
   }
 }
 
+// Split frame: lists the virtual blocks that hold ranks of this GPU's strips (one thread per block), so that k_rng_rank is launched over
+// them only — an empty CTA still costs its launch and two dependent loads: 28 000 of them were most of the ranking time of an 8-way split.
+__global__ void __launch_bounds__(RNG_THREADS) k_rng_own_list(RngLocate * __restrict__ loc, const uint32_t * __restrict__ prefix, unsigned long long n,
+                                                              uint32_t nBlocks, unsigned long long ownPeriod, uint32_t ownWorld, uint32_t ownRank,
+                                                              uint32_t * __restrict__ ownList, uint32_t ownListCap, int * __restrict__ status)
+{
+  const uint32_t v = blockIdx.x * RNG_THREADS + threadIdx.x;
+  bool owned = false;
+  if (v < nBlocks)
+  {
+    const RngBlock b = rngVirtualBlock(v, loc->r0, loc->j0, loc->r1, loc->nb1, loc->off1, loc->seg1, prefix);
+    if (!b.valid) { if (v == nBlocks - 1) *status = 1; }                                   // a third class in one pass: callers chunk below that
+    else
+    {
+      if (v == nBlocks - 1 && b.next < (long long)n) *status = 1;                          // the provisioned blocks do not reach rank n-1
+      owned = b.first < (long long)n && b.next > 0 && b.next > b.first && rngBlockOwned(b.first, b.next, n, ownPeriod, ownWorld, ownRank);
+    }
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, owned);
+  if (m)
+  {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&loc->ownCount, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (owned)
+    {
+      const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+      if (slot < ownListCap) ownList[slot] = v; else *status = 1;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(RNG_THREADS) k_rng_rank(const RngLocate * __restrict__ loc, const uint32_t * __restrict__ prefix,
                                                           uint32_t * __restrict__ stateOut, uint32_t * __restrict__ sampleStates,
                                                           unsigned long long n, unsigned long long ownPeriod, uint32_t ownWorld, uint32_t ownRank,
-                                                          int * __restrict__ status)
+                                                          int * __restrict__ status, uint32_t nBlocks, const uint32_t * __restrict__ ownList)
 {
   // virtual block v of the pass -> block j of class r; ranks of the stream = table prefix + local prefix - off
-  const uint32_t v = blockIdx.x, nb1 = loc->nb1;
-  uint32_t r, j;
-  long long off;
-  if (v < nb1) { r = loc->r0; j = loc->j0 + v; off = (long long)loc->off1; }
-  else         { r = loc->r1; j = v - nb1;     off = -(long long)loc->seg1; }
-  const bool lastBlock = v == gridDim.x - 1;
-  if (j >= RNG_CLASS_BLOCKS)
+  uint32_t v = blockIdx.x;
+  if (ownList)
+  {
+    if (blockIdx.x >= min(loc->ownCount, gridDim.x)) return;     // the grid is the host's upper bound of the list
+    v = ownList[blockIdx.x];
+  }
+  const RngBlock b = rngVirtualBlock(v, loc->r0, loc->j0, loc->r1, loc->nb1, loc->off1, loc->seg1, prefix);
+  const bool lastBlock = v == nBlocks - 1;
+  if (!b.valid)
   {
     if (lastBlock && threadIdx.x == 0) *status = 1;             // a third class in one pass: callers chunk below that
     return;
   }
-  const uint32_t * pre = prefix + r * (RNG_CLASS_BLOCKS + 1);
-  const long long first = (long long)pre[j] - off, next = (long long)pre[j + 1] - off;   // ranks [first, next) start in this block
+  const uint32_t r = b.r, j = b.j;
+  const long long first = b.first, next = b.next;               // ranks [first, next) start in this block
   if (lastBlock && next < (long long)n && threadIdx.x == 0) *status = 1;                  // the provisioned blocks do not reach rank n-1
   if (first >= (long long)n || next <= 0) return;                                         // uniform per CTA
-  if (ownWorld)
-  {
-    // split frames: a CTA whose ranks all lie in one strip of another GPU has nothing to store (the stream-end state is
-    // written by whoever holds rank n-1, so that CTA is never skipped)
-    const unsigned long long lo = (unsigned long long)(first < 0 ? 0 : first), hi = (unsigned long long)(next > (long long)n ? (long long)n : next) - 1ull;
-    const unsigned long long s0 = lo / ownPeriod, s1 = hi / ownPeriod;
-    if (s0 == s1 && (uint32_t)(s0 % ownWorld) != ownRank && hi < n - 1) return;
-  }
+  // split frames without a list (no scratch given): a CTA whose ranks all lie in strips of other GPUs has nothing to store
+  if (ownWorld && !ownList && !rngBlockOwned(first, next, n, ownPeriod, ownWorld, ownRank)) return;
 
   const uint32_t sStart = rngThreadStart(r, j);
   const uint32_t mask = rngThreadMask(sStart, r, j);
@@ -354,6 +416,15 @@ int launchRngTable(uint32_t * counts, uint32_t * prefix, cudaStream_t st)
   return 2;
 }
 
+uint32_t rngOwnBlocksBound(uint64_t n, uint64_t ownPeriod, uint32_t ownWorld, uint32_t nBlocks)
+{
+  // a strip of ownPeriod ranks overlaps at most ownPeriod / 900 + 3 blocks (a block of 2048 triples holds 1072 +- 23 accepted ones:
+  // 900 is 7 sigma below), this GPU owns every ownWorld-th strip, and the block of rank n-1 is always listed
+  const uint64_t strips = (n + ownPeriod - 1) / ownPeriod, mine = (strips + ownWorld - 1) / ownWorld;
+  const uint64_t bound = mine * (ownPeriod / 900 + 3) + 4;
+  return (uint32_t)std::min<uint64_t>(bound, nBlocks);
+}
+
 int launchRngRank(const RngWork & w, cudaStream_t st)
 {
   if (!w.sampleStates)
@@ -361,10 +432,16 @@ int launchRngRank(const RngWork & w, cudaStream_t st)
     k_rng_locate<<<1, RNG_THREADS, 0, st>>>(w.stateIn, w.prefix, (unsigned long long)w.n, w.locate, w.stateOut, w.status);
     return 1;
   }
+  const uint32_t cap = w.ownWorld ? rngOwnBlocksBound(w.n, w.ownPeriod, w.ownWorld, w.nBlocks) : 0u;
+  const bool listed = w.ownWorld && w.ownList && w.ownListCap >= cap;
   k_rng_locate<<<1, RNG_THREADS, 0, st>>>(w.stateIn, w.prefix, (unsigned long long)w.n, w.locate, nullptr, w.status);
-  k_rng_rank<<<w.nBlocks, RNG_THREADS, 0, st>>>(w.locate, w.prefix, w.stateOut, w.sampleStates, (unsigned long long)w.n,
-                                                 (unsigned long long)w.ownPeriod, w.ownWorld, w.ownRank, w.status);
-  return 2;
+  if (listed)
+    k_rng_own_list<<<(w.nBlocks + RNG_THREADS - 1) / RNG_THREADS, RNG_THREADS, 0, st>>>(w.locate, w.prefix, (unsigned long long)w.n, w.nBlocks,
+                                                                                        (unsigned long long)w.ownPeriod, w.ownWorld, w.ownRank, w.ownList, cap, w.status);
+  k_rng_rank<<<listed ? cap : w.nBlocks, RNG_THREADS, 0, st>>>(w.locate, w.prefix, w.stateOut, w.sampleStates, (unsigned long long)w.n,
+                                                                (unsigned long long)w.ownPeriod, w.ownWorld, w.ownRank, w.status, w.nBlocks,
+                                                                listed ? w.ownList : nullptr);
+  return listed ? 3 : 2;
 }
 
 // =====================================================================================================================
