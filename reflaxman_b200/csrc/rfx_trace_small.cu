@@ -49,6 +49,9 @@ namespace rfx
 #ifndef RFX_SMALL_THREADS
 #define RFX_SMALL_THREADS 128
 #endif
+#ifndef RFX_ALIGN_PHASES
+#define RFX_ALIGN_PHASES 1         // single-light scenes: lanes whose hit faces no light idle through the shadow trip (keeps the tile's lanes in one phase)
+#endif
 #ifndef RFX_STRIP_STAGING
 #define RFX_STRIP_STAGING 1        // split frames: 64-byte row-segment stores staged through shared memory (0: the A/B arm, direct 16-byte stores)
 #endif
@@ -349,7 +352,8 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
     {
       // ---- answer of the shadow query for light li, Scene.cpp:125-186
       const Light & L = sc.light[(FEAT & F_LIGHTS) ? li : 0];
-      const bool inShadow = hit.slot >= 0;
+      // (li < 0: the "query" was the idle trip of a hit that faces no light — see below — and has no answer to take)
+      const bool inShadow = hit.slot >= 0 || (RFX_ALIGN_PHASES && !SIG && !(FEAT & F_LIGHTS) && li < 0);
       if (SIG) RFX_SIG(sig, 0x100 + 2 * li + (inShadow ? 1 : 0));
       if (!inShadow)
       {
@@ -405,6 +409,18 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
       if (FEAT & F_LIGHTS) { carryLight = sumLight; carrySpec = sumSpec; }
       shadowQuery = true;
       events += 0x10000u;
+      continue;
+    }
+    if (RFX_ALIGN_PHASES && !SIG && !(FEAT & F_LIGHTS) && !shadowQuery)
+    {
+      // Single-light scenes: a hit that faces no light would finish now and start its next bounce while its neighbours run their
+      // shadow queries — from then on the lanes of the warp are in both phases of the machine on every trip, and every trip executes
+      // the hit set-up AND the shadow answer with part of the lanes.  It sits out one trip instead (a null query: a zero ray fails
+      // every gate; the warp runs the object loops for its neighbours anyway), so that bounce and shadow trips keep alternating
+      // for the whole tile.  Nothing it computes changes.
+      qd = mk(0.0f, 0.0f, 0.0f);
+      shadowQuery = true;
+      li = -1;
       continue;
     }
 

@@ -12,9 +12,7 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 VARIANTS = {
     # name: (defines, force_path)
     "base": ([], 1),
-    "t64": (["RFX_SMALL_THREADS=64", "RFX_SMALL_MINBLOCKS=16"], 1),     # 2-warp CTAs: slots free up per pair of tiles
-    "t32": (["RFX_SMALL_THREADS=32", "RFX_SMALL_MINBLOCKS=32"], 1),     # 1-warp CTAs
-    "t256": (["RFX_SMALL_THREADS=256", "RFX_SMALL_MINBLOCKS=4"], 1),
+    "noalign": (["RFX_ALIGN_PHASES=0"], 1),     # lanes whose hit faces no light start their next bounce at once (round-1 behaviour)
 }
 
 
