@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 W, H, DEPTH = 1920, 1080, 20
 CENSUS_FLOP_PER_PIXEL = 1301.7          # SURVEY.md §8(d), config 2 (our own census build counts 1270.9)
 NCU_RAW_CSV = ("profiles/r2_final/prof_k_trace_small_raw.csv", "profiles/r1_final/prof_k_trace_small_raw.csv")   # ncu --set full, newest first
-UNFUSED_SCALAR_CEILING_TFLOPS = 35.8    # measured: scalar FMUL+FADD issue ceiling (profiles/microbench_r1.jsonl); a balanced FMUL2+FADD2 mix measures 73.1
+UNFUSED_SCALAR_CEILING_TFLOPS = 35.8    # measured: un-fused FMUL+FADD issue ceiling, scalar (35.8) or packed f32x2 on independent chains (36.6): profiles/microbench_r2.jsonl
 RAYS_PER_FRAME_CANONICAL = 7493076      # oracle counters, config 2, seed 12345 (3.6136 rays/pixel); recomputed live when possible
 METRIC = "Mrays/s at 1920x1080, default scene, reflection depth 20 (frames/s alongside)"
 WORKLOAD = "config2: default scene 1920x1080, reflection depth 20, 1 sample/pixel, default camera; a step is frames_per_step successive frames (randDir stream continues)"
@@ -405,10 +405,11 @@ def run_ours(args):
                 "note": "bound is FP32 CUDA-core issue (neither hbm nor tensor: >= 80 flop per mandatory byte); traffic = dram__bytes_read+write of one "
                         "launch, read from the committed ncu --set full raw page (the 8.3 MB ARGB frame stays in the 126 MB L2 until evicted); "
                         "achieved = SURVEY census 1301.7 flop/pixel x 1920x1080 per launch / mean k_trace_small duration (CUDA events on its stream, "
-                        "warm = tiles started in the cost order the previous frame recorded; cold = first frame over a grid, index order); "
+                        "warm = tiles started in the cost order the previous frame recorded; cold = first frame over a grid); "
                         "peak = 2*128*SMs*sm_max_mhz (FFMA; MEASURED_PEAKS.json has no FP32 entry; microbench measured 70.4). The arithmetic "
-                        "must stay un-fused for parity: scalar FMUL+FADD issue tops out at 35.8 TFLOP/s, a balanced packed FMUL2+FADD2 mix at 73.1 "
-                        "(profiles/microbench_r1.jsonl)",
+                        "must stay un-fused for parity: FMUL+FADD tops out at 35.8 TFLOP/s scalar and 36.6 packed (FMUL2/FADD2 on independent chains; "
+                        "a dependent packed pair is contracted into FFMA2 by ptxas even under --fmad=false): profiles/microbench_r2.jsonl, "
+                        "tools/ffma2_contraction_repro.cu; first frame over a grid = middle tile rows first (no recording to replay)",
                 "unfused_scalar_ceiling_tflops": UNFUSED_SCALAR_CEILING_TFLOPS, "frac_of_unfused_scalar_ceiling": achieved / UNFUSED_SCALAR_CEILING_TFLOPS}
 
     cpu = None
