@@ -111,6 +111,12 @@ RFX_API int rfx_skip_samples(rfx_ctx * ctx, uint64_t n_trace_calls);
  * 2^32-state cycle.  out[0] = triples on which they disagree (0 = the decisions are the reference's, by exhaustion),
  * out[1] = triples inside the guard band.  About 20 ms. */
 RFX_API int rfx_selftest_rng(rfx_ctx * ctx, uint64_t out[2]);
+/* diagnostic: every path of a frame starts at the eye (Render.cpp:154-156), so the fast kernel lets a warp's first pass over the
+ * objects skip those whose screen bounds miss its 4x8 pixel tile.  This returns the bounds the library derives for the current
+ * scene (constant-bank scenes only), camera and image size: out[4*i .. 4*i+3] = x0, x1, y0, y1 (inclusive; x0 > x1 = no pixel) of
+ * sphere i (i < 16) or triangle i - 16 (16 <= i < 24), objects in insertion order within their kind; counts = {spheres, triangles}.
+ * A test evaluates Sphere::trace's / Triangle::trace's accept expressions on every pixel against them. */
+RFX_API int rfx_selftest_primary_bounds(rfx_ctx * ctx, int32_t out[96], int32_t counts[2]);
 
 /* ---- Render (reference Render.h:30-41) ----------------------------------------------------------------- */
 RFX_API int rfx_set_image_size(rfx_ctx * ctx, uint32_t width, uint32_t height);   /* Render::setImageSize, Render.cpp:57-80 */

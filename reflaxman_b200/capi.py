@@ -52,6 +52,7 @@ SYMBOLS = [
     ("rfx_get_seeds", C.c_int, [C.c_void_p, _u32p]),
     ("rfx_skip_samples", C.c_int, [C.c_void_p, C.c_uint64]),
     ("rfx_selftest_rng", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    ("rfx_selftest_primary_bounds", C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("rfx_set_image_size", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     ("rfx_render_begin", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("rfx_render_next", C.c_int, [C.c_void_p, C.c_uint32]),
@@ -204,6 +205,15 @@ class Context:
         out = (C.c_uint64 * 2)()
         self._ck(self.L.rfx_selftest_rng(self.h, out), "rfx_selftest_rng")
         return int(out[0]), int(out[1])
+
+    def selftest_primary_bounds(self):
+        """Screen bounds of the scene's objects for the primary rays of the current camera and image size:
+        (sphere rectangles [nS][4], triangle rectangles [nT][4]) as x0, x1, y0, y1 inclusive (x0 > x1: no pixel)."""
+        out = (C.c_int32 * 96)()
+        cnt = (C.c_int32 * 2)()
+        self._ck(self.L.rfx_selftest_primary_bounds(self.h, out, cnt), "rfx_selftest_primary_bounds")
+        a = np.ctypeslib.as_array(out).reshape(24, 4).copy()
+        return a[:cnt[0]], a[16:16 + cnt[1]]
 
     def skip_samples(self, n):
         self._ck(self.L.rfx_skip_samples(self.h, n), "rfx_skip_samples")

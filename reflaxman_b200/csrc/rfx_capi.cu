@@ -947,6 +947,30 @@ int rfx_selftest_rng(rfx_ctx * ctx, uint64_t out[2])
   return RFX_OK;
 }
 
+int rfx_selftest_primary_bounds(rfx_ctx * ctx, int32_t out[96], int32_t counts[2])
+{
+  if (!ctx || !out || !counts) return RFX_ERR_ARG;
+  if (!ctx->W || !ctx->H) return fail(ctx, RFX_ERR_ARG, "rfx_selftest_primary_bounds: image size not set");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = useStream(ctx, ctx->stream)) != RFX_OK) return rc;
+  if ((rc = uploadScene(ctx, ctx->stream)) != RFX_OK) return rc;
+  if (!ctx->smallOk) return fail(ctx, RFX_ERR_ARG, "rfx_selftest_primary_bounds: the scene does not fit the constant bank");
+  FrameParams fp;
+  memset(&fp, 0, sizeof(fp));
+  memcpy(fp.eye, ctx->eye, sizeof(fp.eye));
+  memcpy(fp.view, ctx->view, sizeof(fp.view));
+  fp.rz = float(ctx->W) / 2.0f / tanf(ctx->fov / 2.0f);
+  fp.wHalf = ctx->W / 2.0f;
+  fp.hHalf = ctx->H / 2.0f;
+  fp.W = ctx->W; fp.H = ctx->H;
+  const PrimaryCull pc = makePrimaryCull(ctx->small, fp);
+  static_assert(sizeof(pc.rect) == 96 * sizeof(int32_t), "24 rectangles of 4 ints");
+  memcpy(out, pc.rect, sizeof(pc.rect));
+  counts[0] = ctx->small.nS; counts[1] = ctx->small.nT;
+  return RFX_OK;
+}
+
 int rfx_skip_samples(rfx_ctx * ctx, uint64_t n)
 {
   if (!ctx) return RFX_ERR_ARG;

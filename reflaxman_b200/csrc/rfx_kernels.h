@@ -107,6 +107,13 @@ int launchTraceBlobRays(const void * sceneBlob, int n, const float * origins, co
 int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st, uint32_t * fastGrid = nullptr);
 // CTA count the fast kernel would use for this work, 0 if the work does not qualify for it
 uint32_t fastGridSize(const TraceWork & w);
+// per launch of the fast kernel: pixel rectangles outside of which no primary ray can hit sphere i (rect[i]) / triangle k
+// (rect[SMALL_MAX_SPHERES + k]); rfx_trace_small.cu has the derivation
+struct PrimaryCull
+{
+  int4 rect[SMALL_MAX_SPHERES + SMALL_MAX_TRIS];   // x0, x1, y0, y1 (inclusive, frame pixels); x0 > x1: no pixel
+};
+PrimaryCull makePrimaryCull(const SmallScene & sc, const FrameParams & fp);
 
 // ---- K3: resolve (imagePixel + argb) ---------------------------------------------------------------------------
 int launchResolve(const float * image, uint64_t nPixels, int additiveCounter, float * rgbfOut, uint32_t * argbOut, cudaStream_t st);

@@ -55,6 +55,12 @@ namespace rfx
 #ifndef RFX_STRIP_STAGING
 #define RFX_STRIP_STAGING 1        // split frames: 64-byte row-segment stores staged through shared memory (0: the A/B arm, direct 16-byte stores)
 #endif
+#ifndef RFX_PRIMARY_CULL
+#define RFX_PRIMARY_CULL 1         // the first query of a path (origin = eye) skips the object-loop trips whose screen bounds miss the warp's tile
+#endif
+#if RFX_PRIMARY_CULL && RFX_SPHERE_GROUP != 4
+#error "RFX_PRIMARY_CULL ranges are in sphere quads: RFX_SPHERE_GROUP must be 4"
+#endif
 #ifndef RFX_SMALL_MINBLOCKS
 #define RFX_SMALL_MINBLOCKS 8      // fast kernel: 64 registers, no spills, 32 warps per SM
 #endif
@@ -86,8 +92,12 @@ __device__ __forceinline__ void considerHit(Best & best, float dist, int slot, i
 // All objects against one ray.  `skip` is the slot the query ignores (the shadow loop's `*obj != hitObject`,
 // Scene.cpp:135; -1 = none).  anyHit: the caller only asks whether something is hit (shadow query), so a lane that has
 // found an occluder stops entering the sqrt/divide tails.
-template <int FEAT>
-__device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d, int skip, bool anyHit, Best & best)
+// The object loops run over [range.s0, range.s1) of the sphere quads and [range.t0, range.t1) of the triangles (byte offsets):
+// everything for every query but the first of a path, whose tile may see only part of the scene (PrimaryCull below).
+struct ObjRange { int s0, s1, t0, t1; };
+
+template <int FEAT, bool RANGED>
+__device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d, int skip, bool anyHit, Best & best, const ObjRange range)
 {
   const float a = vsqlen(d);                                          // Sphere.cpp:50
   const float r2x = d.x * 2.0f, r2y = d.y * 2.0f, r2z = d.z * 2.0f;   // 2.0f * ray, Sphere.cpp:51
@@ -127,13 +137,13 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
       }                                                                                      \
     }
   const int endOff = sc.nS << 4;
-  int off = 0;
+  int off = RANGED ? range.s0 : 0;
   // Several spheres per trip: their reject chains are independent (ILP for a scheduler that holds ~7 warps), they share the
   // loop bookkeeping, and ONE divergent region gates all their tails (the common case — no lane passes any gate — costs one
   // branch).  The discriminants of a trip are evaluated before its tails, so an any-hit lane that closes in an earlier tail
   // (a4 becomes NaN) must not enter a later one.
 #if RFX_SPHERE_GROUP == 4
-  const int endQuad = endOff & ~63;
+  const int endQuad = RANGED ? range.s1 : (endOff & ~63);
 #pragma unroll 1
   for (; off != endQuad; off += 64)
   {
@@ -151,6 +161,7 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
       if (g3 && a4 == a4) RFX_SPHERE_TAIL(off + 48, b3, disc3)
     }
   }
+  if (RANGED) off = endOff & ~63;          // the spheres past the last whole quad are tested on every query
 #endif
 #if RFX_SPHERE_GROUP >= 2
   const int endPair = endOff & ~31;
@@ -187,7 +198,7 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
   const char * triBase = reinterpret_cast<const char *>(sc.triPk);
   const char * triOrd = reinterpret_cast<const char *>(&sc.mat[SM_TRI_BIT].order);
   const int skipTri = (skip - SM_TRI_BIT) * 48;
-  const int endTri = sc.nT * 48;
+  const int endTri = RANGED ? range.t1 : sc.nT * 48;
   // (a zero oz — a ray that starts exactly on the plane, common for rays leaving a floor triangle towards its coplanar
   // neighbour — would give t = 0 and fail in the tail, but 0 / rz takes div.rn's 30-instruction slow path: the gate rejects it)
 #define RFX_TRI_REJECT(OFF, A, B, PX, PY, PZ, OZ, RZ)                                         \
@@ -222,7 +233,7 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
         }                                                                                     \
       }                                                                                       \
     }
-  int toff = 0;
+  int toff = RANGED ? range.t0 : 0;
 #pragma unroll 1
   for (; toff != endTri; toff += 48)
   {
@@ -259,8 +270,10 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
 
 // ---- Scene::trace (reference Scene.cpp:73-236) ------------------------------------------------------------------------
 // `events` counts bounce-loop iterations in its low half and shadow rays in its high half (one register instead of two).
-template <bool SIG, int FEAT>
-__device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ray, int reflNumber, V3 randDir, uint32_t & events, uint32_t & sig)
+// RANGED: `first` is the object range of the path's first query (the tile's PrimaryCull answer); every later query sees everything.
+template <bool SIG, int FEAT, bool RANGED = false>
+__device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ray, int reflNumber, V3 randDir, uint32_t & events, uint32_t & sig,
+                                         const ObjRange first = ObjRange())
 {
   V3 mul = mk(1.0f, 1.0f, 1.0f);
   V3 pix = mk(0.0f, 0.0f, 0.0f);
@@ -279,12 +292,14 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
   float normLen = 0.0f, reflectLen = 0.0f, mrefl = 0.0f;
   float rfs = 0.0f;         // weight of the reflected continuation (Scene.cpp:196 / :207), negated for metals (one register
                             // for the weight and the material type; the weight is in [0.2, 1], never zero)
+  ObjRange range = first;
 
   for (;;)
   {
     Best hit;
     hit.dist = FLT_MAX; hit.slot = -1; hit.order = 0x7FFFFFFF; hit.t = 0; hit.u = 0; hit.v = 0;
-    intersectSmall<FEAT>(sc, qo, qd, shadowQuery ? hslot : -1, shadowQuery, hit);
+    intersectSmall<FEAT, RANGED>(sc, qo, qd, shadowQuery ? hslot : -1, shadowQuery, hit, range);
+    if (RANGED) { range.s0 = 0; range.s1 = (sc.nS << 4) & ~63; range.t0 = 0; range.t1 = sc.nT * 48; }   // rematerialised from the constant bank
 
     V3 sumLight = (FEAT & F_LIGHTS) ? carryLight : mk(0.0f, 0.0f, 0.0f);
     V3 sumSpec = (FEAT & F_LIGHTS) ? carrySpec : mk(0.0f, 0.0f, 0.0f);
@@ -448,6 +463,136 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
   return pix;
 }
 
+// ---- screen bounds of the objects for the primary rays ---------------------------------------------------------------
+// Every path of a launch starts at the eye, and a warp owns a 4x8 pixel tile: most tiles see none of the spheres and a part
+// of the triangles.  Per launch the host bounds, for each sphere and triangle of the scene, the pixels whose primary ray can pass
+// that object's hit test (a rectangle, conservative: float noise of the test, SSAA sub-samples and additive jitter are inside
+// the margins).  A warp compares its tile with the rectangles (one object per lane, one ballot) and its FIRST pass over the
+// objects runs only the sphere quads / triangles from the first to the last candidate.  A trip that is skipped could not have
+// produced a hit, so nothing a path computes changes; later queries of the path (shadow rays, bounces) see every object.
+// tests/test_oracle.py::test_primary_bounds_are_conservative evaluates the kernel's float expressions on every pixel for
+// random cameras (inside spheres, under the floor, looking away) against rfx_selftest_primary_bounds.
+// (struct PrimaryCull: rfx_kernels.h)
+constexpr int CULL_LO = -(1 << 30), CULL_HI = 1 << 30;
+constexpr double CULL_PIX_MARGIN = 3.0;            // sub-samples and jitter reach < 2 pixels past the pixel origin (Render.cpp:177-184)
+
+static int4 cullFull() { return make_int4(CULL_LO, CULL_HI, CULL_LO, CULL_HI); }
+static int4 cullNone() { return make_int4(1, 0, 1, 0); }
+static int cullClamp(double v)
+{
+  if (!(v == v)) return 0;
+  return v <= (double)CULL_LO ? CULL_LO : v >= (double)CULL_HI ? CULL_HI : (int)v;
+}
+
+// A sphere: the tangent planes through the eye that contain the camera's y (x) axis bound its projection in x (y).  The test the
+// kernel runs is the float discriminant of Sphere.cpp:49-53, whose rounding noise lets a ray pass that misses the sphere by up to
+// sqrt(r^2 + 4e-7 |w|^2) - r: the radius is inflated by 1e-3 r + 1e-3 |w|.
+static int4 cullSphere(const double * c0, const double * c1, const double * c2, const double * eye, double rz, double wHalf, double hHalf, const float4 & s)
+{
+  const double w[3] = { (double)s.x - eye[0], (double)s.y - eye[1], (double)s.z - eye[2] };
+  const double wl = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  const double r = sqrt(s.w > 0.0f ? (double)s.w : 0.0);
+  if (!(wl < 1e300) || !(r < 1e300)) return cullFull();
+  const double rEff = r * 1.001 + 1e-3 * wl + 1e-30;
+  const double wx = c0[0] * w[0] + c0[1] * w[1] + c0[2] * w[2], wy = c1[0] * w[0] + c1[1] * w[1] + c1[2] * w[2], wz = c2[0] * w[0] + c2[1] * w[1] + c2[2] * w[2];
+  int out[4];
+  for (int ax = 0; ax < 2; ax++)
+  {
+    const double a = ax ? wy : wx, half = ax ? hHalf : wHalf;
+    const double d2 = sqrt(a * a + wz * wz);
+    if (d2 <= rEff) { out[2 * ax] = CULL_LO; out[2 * ax + 1] = CULL_HI; continue; }
+    const double th = atan2(a, wz), al = asin(rEff / d2), lim = 1.5707963267948966 - 1e-4;
+    const double lo = th - al, hi = th + al;
+    if (hi <= -lim || lo >= lim) return cullNone();          // behind the eye in this projection
+    out[2 * ax] = lo <= -lim ? CULL_LO : cullClamp(floor(rz * tan(lo) + half - CULL_PIX_MARGIN));
+    out[2 * ax + 1] = hi >= lim ? CULL_HI : cullClamp(ceil(rz * tan(hi) + half + CULL_PIX_MARGIN));
+  }
+  return make_int4(out[0], out[1], out[2], out[3]);
+}
+
+// A triangle: the edges come back out of axTrans (its inverse holds v2-v0 | v1-v0 | -n), the triangle is widened in barycentric
+// space by the noise of u = ox + t*rx (Triangle.cpp:65-66), clipped against a near plane so close to the eye that what it cuts
+// off projects outside the image, and projected.
+static int4 cullTriangle(const double * c0, const double * c1, const double * c2, const double * eye, double rz, double wHalf, double hHalf,
+                         double W, double H, const Triangle & tr)
+{
+  double A[9];
+  for (int i = 0; i < 9; i++) { A[i] = (double)tr.ax[i]; if (!(fabs(A[i]) < 1e300)) return cullFull(); }
+  const double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+  if (!(fabs(det) > 1e-30) || !(fabs(det) < 1e300)) return cullFull();
+  // columns of the inverse
+  const double ea[3] = { (A[4] * A[8] - A[5] * A[7]) / det, -(A[3] * A[8] - A[5] * A[6]) / det, (A[3] * A[7] - A[4] * A[6]) / det };
+  const double eb[3] = { -(A[1] * A[8] - A[2] * A[7]) / det, (A[0] * A[8] - A[2] * A[6]) / det, -(A[0] * A[7] - A[1] * A[6]) / det };
+  const double nn[3] = { (A[1] * A[5] - A[2] * A[4]) / det, -(A[0] * A[5] - A[2] * A[3]) / det, (A[0] * A[4] - A[1] * A[3]) / det };
+  const double v0[3] = { (double)tr.v0[0], (double)tr.v0[1], (double)tr.v0[2] };
+  const double ev[3] = { eye[0] - v0[0], eye[1] - v0[1], eye[2] - v0[2] };
+  const double la = sqrt(ea[0] * ea[0] + ea[1] * ea[1] + ea[2] * ea[2]), lb = sqrt(eb[0] * eb[0] + eb[1] * eb[1] + eb[2] * eb[2]);
+  const double nl = sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+  const double emin = la < lb ? la : lb;
+  if (!(nl > 0.0) || !(emin > 0.0) || !(la < 1e300) || !(lb < 1e300) || !(nl < 1e300)) return cullFull();
+  const double dist = fabs(nn[0] * ev[0] + nn[1] * ev[1] + nn[2] * ev[2]) / nl;     // lower bound of the distance from the eye to the triangle
+  const double reach = sqrt(ev[0] * ev[0] + ev[1] * ev[1] + ev[2] * ev[2]) + la + lb;
+  if (!(dist > 1e-6 * reach) || !(reach < 1e300)) return cullFull();
+  const double mu = 1e-3 + 1e-5 * reach / emin;
+  const double dx = (wHalf > W - wHalf ? wHalf : W - wHalf), dy = (hHalf > H - hHalf ? hHalf : H - hHalf);
+  const double D = sqrt(dx * dx + dy * dy) + 8.0;
+  const double znear = 0.5 * dist / sqrt(1.0 + (2.0 * D / rz) * (2.0 * D / rz));
+  const double uv[3][2] = { { -mu, -mu }, { 1.0 + 2.0 * mu, -mu }, { -mu, 1.0 + 2.0 * mu } };
+  double cam[3][3];
+  for (int i = 0; i < 3; i++)
+  {
+    double p[3];
+    for (int k = 0; k < 3; k++) p[k] = uv[i][0] * ea[k] + uv[i][1] * eb[k] - ev[k];     // point - eye
+    cam[i][0] = c0[0] * p[0] + c0[1] * p[1] + c0[2] * p[2];
+    cam[i][1] = c1[0] * p[0] + c1[1] * p[1] + c1[2] * p[2];
+    cam[i][2] = c2[0] * p[0] + c2[1] * p[1] + c2[2] * p[2];
+  }
+  double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+  int n = 0;
+  auto take = [&](double px, double py, double pz)
+  {
+    const double sx = rz * px / pz + wHalf, sy = rz * py / pz + hHalf;
+    x0 = sx < x0 ? sx : x0; x1 = sx > x1 ? sx : x1; y0 = sy < y0 ? sy : y0; y1 = sy > y1 ? sy : y1;
+    n++;
+  };
+  for (int i = 0; i < 3; i++)
+  {
+    const double * a = cam[i], * b = cam[(i + 1) % 3];
+    const bool ina = a[2] >= znear, inb = b[2] >= znear;
+    if (ina) take(a[0], a[1], a[2]);
+    if (ina != inb)
+    {
+      const double t = (znear - a[2]) / (b[2] - a[2]);
+      take(a[0] + t * (b[0] - a[0]), a[1] + t * (b[1] - a[1]), znear);
+    }
+  }
+  if (!n) return cullNone();
+  if (!(x0 == x0) || !(x1 == x1) || !(y0 == y0) || !(y1 == y1)) return cullFull();
+  return make_int4(cullClamp(floor(x0 - CULL_PIX_MARGIN)), cullClamp(ceil(x1 + CULL_PIX_MARGIN)), cullClamp(floor(y0 - CULL_PIX_MARGIN)), cullClamp(ceil(y1 + CULL_PIX_MARGIN)));
+}
+
+PrimaryCull makePrimaryCull(const SmallScene & sc, const FrameParams & fp)
+{
+  PrimaryCull pc;
+  for (int i = 0; i < SMALL_MAX_SPHERES + SMALL_MAX_TRIS; i++) pc.rect[i] = cullFull();
+  // ray = rx * c0 + ry * c1 + rz * c2 (Render.cpp:154-156): the bounds need an orthonormal camera (Camera.cpp:24-36 builds one)
+  double c[3][3], eye[3];
+  for (int j = 0; j < 3; j++) { eye[j] = (double)fp.eye[j]; for (int i = 0; i < 3; i++) c[j][i] = (double)fp.view[3 * i + j]; }
+  bool ok = fp.rz > 0.0f && fp.rz < 1e30f && fabs(eye[0]) < 1e30 && fabs(eye[1]) < 1e30 && fabs(eye[2]) < 1e30;
+  for (int a = 0; a < 3 && ok; a++)
+    for (int b = 0; b < 3; b++)
+    {
+      const double dot = c[a][0] * c[b][0] + c[a][1] * c[b][1] + c[a][2] * c[b][2];
+      if (!(fabs(dot - (a == b ? 1.0 : 0.0)) < 1e-4)) ok = false;
+    }
+  if (!ok) return pc;
+  for (int i = 0; i < sc.nS && i < SMALL_MAX_SPHERES; i++)
+    pc.rect[i] = cullSphere(c[0], c[1], c[2], eye, (double)fp.rz, (double)fp.wHalf, (double)fp.hHalf, sc.sph[i]);
+  for (int k = 0; k < sc.nT && k < SMALL_MAX_TRIS; k++)
+    pc.rect[SMALL_MAX_SPHERES + k] = cullTriangle(c[0], c[1], c[2], eye, (double)fp.rz, (double)fp.wHalf, (double)fp.hHalf, (double)fp.W, (double)fp.H, sc.tri[k]);
+  return pc;
+}
+
 // ---- K2 ----------------------------------------------------------------------------------------------------------------
 constexpr int SMALL_THREADS = RFX_SMALL_THREADS;
 
@@ -485,7 +630,7 @@ template <int FEAT, bool MULTI, bool STRIPS>
 __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS) k_trace_small(const __grid_constant__ SmallScene sc, const __grid_constant__ FrameParams fp,
                                                                const uint32_t * __restrict__ sampleStates, uint32_t * __restrict__ argbOut,
                                                                unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1,
-                                                               const TileOrder ord, float * __restrict__ image)
+                                                               const TileOrder ord, float * __restrict__ image, const __grid_constant__ PrimaryCull pc)
 {
   // which tile group does this CTA render: index order, or the previous launch's cost order (expensive classes first)
   uint32_t bx = blockIdx.x, by = blockIdx.y;
@@ -534,6 +679,21 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
   }
   const uint32_t y = yTop + (lane / RFX_TILE_W);
   const bool valid = x < fp.W && y < y1;
+  // which objects can the primary rays of this warp's tile hit: lane i asks for object i (spheres 0..15, triangles 16..23)
+  ObjRange first;
+  first.s0 = 0; first.s1 = 0; first.t0 = 0; first.t1 = 0;
+  if (RFX_PRIMARY_CULL)
+  {
+    const int tx0 = (int)(xCta + warp * RFX_TILE_W), ty0 = (int)yTop;
+    const int4 r = pc.rect[lane < SMALL_MAX_SPHERES + SMALL_MAX_TRIS ? lane : 0];
+    const bool seen = lane < SMALL_MAX_SPHERES + SMALL_MAX_TRIS && tx0 + (int)RFX_TILE_W - 1 >= r.x && tx0 <= r.y && ty0 + (int)RFX_TILE_H - 1 >= r.z && ty0 <= r.w;
+    const uint32_t m = __ballot_sync(0xffffffffu, seen);
+    const uint32_t ms = m & ((1u << (sc.nS & ~3)) - 1u);                 // spheres of whole quads (the rest is always tested)
+    const uint32_t mq = (ms | (ms >> 1) | (ms >> 2) | (ms >> 3)) & 0x1111u;   // bit 4q: quad q has a candidate
+    if (mq) { first.s0 = (__ffs(mq) - 1) << 4; first.s1 = ((31 - __clz(mq)) << 4) + 64; }
+    const uint32_t mt = (m >> SMALL_MAX_SPHERES) & ((1u << sc.nT) - 1u);
+    if (mt) { first.t0 = (__ffs(mt) - 1) * 48; first.t1 = (32 - __clz(mt)) * 48; }
+  }
   uint32_t events = 0;                                                   // MULTI: of the longest call in the low half (cost class)
   uint32_t nBounces = 0, nShadow = 0;                                    // MULTI: totals over the calls
   uint32_t packed = 0, qOut = 0;
@@ -549,7 +709,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
     V3 rd;
     rngTriple(s, rd.x, rd.y, rd.z);
     uint32_t sig = 0;
-    const V3 c = traceSmall<false, FEAT>(sc, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, events, sig);
+    const V3 c = traceSmall<false, FEAT, RFX_PRIMARY_CULL != 0>(sc, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, events, sig, first);
 #ifdef RFX_DEBUG_DEPTH
     packed = events;           // debug build (tools/depth_stats.py): bounce-loop iterations | shadow rays << 16 instead of the colour
 #else
@@ -620,7 +780,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
                         (px * fp.view[3] + py * fp.view[4]) + fp.rz * fp.view[5],
                         (px * fp.view[6] + py * fp.view[7]) + fp.rz * fp.view[8]);
       uint32_t ev = 0, sig = 0;
-      const V3 c = traceSmall<false, FEAT>(sc, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, ev, sig);
+      const V3 c = traceSmall<false, FEAT, RFX_PRIMARY_CULL != 0>(sc, mk(fp.eye[0], fp.eye[1], fp.eye[2]), ray, fp.reflNum, rd, ev, sig, first);
       fin = vadd(fin, c);
       nBounces += ev & 0xFFFFu; nShadow += ev >> 16;
       events = max(events, ev & 0xFFFFu);
@@ -862,7 +1022,8 @@ int launchTraceSmall(const SmallScene & sc, const TraceWork & w, cudaStream_t st
         const bool lean = !texels && sc.nP == 0 && sc.nL <= 1;
         const bool multi = fp.sampleNum != 1 || fp.jitter || w.image != nullptr;
         const uint32_t y0 = (uint32_t)(fp.p0 / fp.W), y1 = (uint32_t)(fp.p1 / fp.W);
-#define RFX_LAUNCH_SMALL(F, M, S, IMG) k_trace_small<F, M, S><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.order, IMG)
+        const PrimaryCull pc = RFX_PRIMARY_CULL ? makePrimaryCull(sc, fp) : PrimaryCull();
+#define RFX_LAUNCH_SMALL(F, M, S, IMG) k_trace_small<F, M, S><<<grid, SMALL_THREADS, 0, st>>>(sc, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.order, IMG, pc)
         if (fp.stripWorld)
         {
           if (lean && !multi) RFX_LAUNCH_SMALL(0, false, true, nullptr);

@@ -490,3 +490,72 @@ def test_stream_skip_matches_serial_stream(capi, oracle):
         assert c.get_seeds()[0] == d.get_seeds()[0]
     finally:
         c.close(); d.close()
+
+
+def _primary_proto():
+    import os
+    import sys
+    tools = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
+    if tools not in sys.path:
+        sys.path.insert(0, tools)
+    import primary_cull_proto
+    return primary_cull_proto
+
+
+@pytest.mark.parametrize("which", ["default", "mixed"])
+def test_primary_bounds_are_conservative(capi, which):
+    """The fast kernel lets a warp's first pass over the objects skip what its 4x8 tile cannot see: per launch the library bounds, for
+    every sphere and triangle, the pixels whose primary ray can pass that object's test.  For cameras all over the place (orbit, inside
+    spheres, under the floor, looking away, fov 0.3..2.6) the accept expressions of Sphere.cpp:49-57 / Triangle.cpp:56-68, evaluated in
+    float32 op for op on every pixel (and on the far corner of its SSAA / jitter footprint), never accept outside the rectangle."""
+    P = _primary_proto()
+    scene = S.default_scene() if which == "default" else _mixed_scene()
+    sph, tris = P.scene_arrays(scene)
+    W, H = 320, 180
+    c = capi.Context(0)
+    try:
+        c.load_scene(scene); c.set_image_size(W, H)
+        culled = 0
+        for eye, view, fov in P.random_cameras(60, 11 if which == "default" else 12, sph):
+            c.set_camera((eye, view, fov))
+            srect, trect = c.selftest_primary_bounds()
+            assert len(srect) == len(sph) and len(trect) == len(tris)
+            P.assert_inside(eye, view, fov, W, H, sph, tris, srect, trect)
+            culled += sum(1 for r in list(srect) + list(trect) if r[0] > 0 or r[1] < W - 1 or r[2] > 0 or r[3] < H - 1)
+        assert culled > 100, culled          # the bounds do exclude something (they are not all "whole image")
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("which", ["default", "mixed"])
+def test_primary_cull_leaves_every_frame_identical(capi, which):
+    """Frames of the fast kernel (tiles skip the objects outside their primary bounds) against the general kernel (signature run:
+    every query sees every object) for the same cameras: identical ARGB, identical ray counts; the same with 2x2 SSAA through the
+    Render API (the MULTI instantiation shares the tile's answer between the sub-samples)."""
+    P = _primary_proto()
+    scene = S.default_scene() if which == "default" else _mixed_scene()
+    sph, _ = P.scene_arrays(scene)
+    W, H = 200, 120
+    cams = P.random_cameras(28, 21, sph)
+    a = capi.Context(0)
+    b = capi.Context(0)
+    try:
+        for c in (a, b):
+            c.load_scene(scene); c.set_seeds(5, 5); c.set_image_size(W, H)
+        b.enable_signatures(True)
+        fast = a.render_frames(cams, 12)
+        st = a.stats()
+        assert st["launches_small_fast"] == len(cams) and st["launches_small_any"] == 0, st
+        for k, cam in enumerate(cams):
+            b.render(cam, 12)
+            assert np.array_equal(b.read_argb(), fast[k]), "camera %d" % k
+        assert a.stats()["rays"] == b.stats()["rays"]
+        b.enable_signatures(False)
+        for cam in cams[::5]:
+            a.render(cam, 6, samples=2)
+            b.enable_signatures(True)
+            b.render(cam, 6, samples=2)
+            b.enable_signatures(False)
+            assert np.array_equal(a.read_argb(), b.read_argb())
+    finally:
+        a.close(); b.close()

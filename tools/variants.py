@@ -12,7 +12,7 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 VARIANTS = {
     # name: (defines, force_path)
     "base": ([], 1),
-    "noalign": (["RFX_ALIGN_PHASES=0"], 1),     # lanes whose hit faces no light start their next bounce at once (round-1 behaviour)
+    "nocull": (["RFX_PRIMARY_CULL=0"], 1),      # every query of a path walks every object (the kernel before the primary screen bounds)
 }
 
 
