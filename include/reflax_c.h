@@ -55,6 +55,7 @@ typedef struct rfx_stats
   /* K2 launches by kernel family: constant-bank fast kernel (k_trace_small<FEAT, MULTI>), constant-bank general kernel
    * (k_trace_small_any), blob batch kernel (k_trace_blob<MULTI>), blob general kernel (k_trace) */
   uint64_t launches_small_fast, launches_small_any, launches_blob_fast, launches_blob_any;
+  uint64_t light_grids;     /* lights of the uploaded scene whose shadow queries use a candidate grid (not a counter: survives rfx_stats_reset) */
 } rfx_stats;
 
 typedef struct rfx_device_info
@@ -179,7 +180,9 @@ RFX_API int rfx_enable_profiling(rfx_ctx * ctx, int on);
  * tiles, the rest from a path queue (k = the value, default 2; 0 = the single tile kernel).  "blob_smem_bvh": the queue-driven
  * kernel keeps a small sphere hierarchy in shared memory (default 1).  "tile_order_period": the cost-ordered tile scheduling of the
  * constant-bank fast kernel records the tiles' cost classes on every k-th launch over the same grid and replays the last recording
- * in between (default 8).  Frames are bit-identical under every setting. */
+ * in between (default 8).  "light_grids": scenes with a sphere hierarchy answer the shadow queries of far lights from a 2-D grid of
+ * candidate spheres across the light's direction instead of walking the hierarchy (default 1).  Frames are bit-identical under
+ * every setting. */
 RFX_API int rfx_set_option(rfx_ctx * ctx, const char * name, int64_t value);
 /* kernel selection: 0 = automatic (constant-bank kernels when the scene fits, the blob kernels otherwise),
  * 1 = constant-bank kernel if it fits, 2 = always the blob kernels (tile / wavefront kernels for row-aligned slices, the general

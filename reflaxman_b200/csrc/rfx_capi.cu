@@ -147,6 +147,13 @@ struct rfx_ctx
   int bvhDepth = 0;                         // depth of the hierarchy in dBvhNodes (0: none)
   uint32_t bvhFloat4 = 0;                   // SceneHeader::bvhFloat4 of the uploaded blob
   bool blobSmemBvh = true;                  // rfx_set_option "blob_smem_bvh"
+  // shadow-ray candidate grids of the far lights (LightGrid, rfx_types.h): one allocation each for the headers, the cell offsets and the items
+  LightGrid * dLightGrids = nullptr; size_t lightGridsCap = 0;
+  uint32_t * dGridCells = nullptr; size_t gridCellsCap = 0;
+  float4 * dGridSpheres = nullptr; size_t gridSpheresCap = 0;
+  int * dGridIndex = nullptr; size_t gridIndexCap = 0;
+  bool lightGridsOn = true;                 // rfx_set_option "light_grids"
+  int lightGridsBuilt = 0;                  // lights of the uploaded scene that have a grid
   int bvhMode = 0;                          // 0 auto (spheres > 32), 1 always, 2 never — tests compare both
 
   // ---- camera + render state (reference Render.h:9-27)
@@ -237,6 +244,126 @@ Material makeMaterial(int mtype, const float rgb[3], float refl, float transp, i
 }
 
 // flatten the host scene into the blob layout described in rfx_types.h and upload it
+// ---- shadow-ray candidate grids (LightGrid) ---------------------------------------------------------------------------------------
+// A shadow ray (Scene.cpp:129) runs from a drop point P — a point of some object, so inside the objects' bounding box B — to
+// L + radius * randDir, |randDir| <= 1.  For a light far from the scene all those rays are nearly parallel to l = (L - centre(B)) / |..|:
+// the sine of their angle to l is at most sigma = (diag(B)/2 + radius) / (|L - centre(B)| - diag(B)/2 - radius).  Project everything
+// along l onto a plane.  The exact test (Sphere.cpp:49-57) can only report sphere (C, r) when the ray's line passes within r + m of C
+// (m: the rounding-noise bound the hierarchy's box margins use), at a point X = P + s * dir, s > 0; then
+//     |proj(C) - proj(P)|  <=  |C - X| + s * sigma  <=  r + m + sigma * s,
+// and s is bounded because P must lie in B: C - s*l is within r + m + 1.01 sigma diag(B) of P, so s is at most the distance from C
+// backwards along l to the boundary of B inflated by that much.  The grid cell of proj(P) therefore lists every sphere a shadow ray
+// from P can hit; the any-hit query tests that list with the reference's exact arithmetic instead of walking the hierarchy, and its
+// answer — is the light occluded — is the same.  (Triangles and planes are few and are tested directly, as before.)
+struct LightGridHost
+{
+  LightGrid g;
+  std::vector<uint32_t> cellStart;
+  std::vector<float4> spheres;
+  std::vector<int> index;
+};
+
+bool buildLightGrid(const Light & L, const std::vector<const HostObj *> & sph, const std::vector<BvhPrim> & prims, const double blo[3], const double bhi[3], LightGridHost & out)
+{
+  const double cb[3] = { 0.5 * (blo[0] + bhi[0]), 0.5 * (blo[1] + bhi[1]), 0.5 * (blo[2] + bhi[2]) };
+  const double ext[3] = { bhi[0] - blo[0], bhi[1] - blo[1], bhi[2] - blo[2] };
+  const double diag = sqrt(ext[0] * ext[0] + ext[1] * ext[1] + ext[2] * ext[2]);
+  double l[3] = { (double)L.ox - cb[0], (double)L.oy - cb[1], (double)L.oz - cb[2] };
+  const double D = sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+  const double rad = fabs((double)L.radius) * (1.0 + 1e-5);
+  if (!(D < 1e300) || !(rad < 1e300) || !(diag > 0.0)) return false;
+  const double lateral = 0.5 * diag + rad;
+  if (!(D > 8.0 * lateral)) return false;                       // the light is inside or near the scene: its rays are no bundle
+  const double sigma = lateral / (D - lateral) * 1.001 + 1e-6;   // + the float evaluation of the ray on the device
+  for (int k = 0; k < 3; k++) l[k] /= D;
+  // plane axes
+  const int minAxis = fabs(l[0]) <= fabs(l[1]) && fabs(l[0]) <= fabs(l[2]) ? 0 : fabs(l[1]) <= fabs(l[2]) ? 1 : 2;
+  double e[3] = { 0, 0, 0 }; e[minAxis] = 1.0;
+  double u[3] = { l[1] * e[2] - l[2] * e[1], l[2] * e[0] - l[0] * e[2], l[0] * e[1] - l[1] * e[0] };
+  const double ul = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+  for (int k = 0; k < 3; k++) u[k] /= ul;
+  const double v[3] = { l[1] * u[2] - l[2] * u[1], l[2] * u[0] - l[0] * u[2], l[0] * u[1] - l[1] * u[0] };
+  // per sphere: disc centre and radius on the plane
+  const size_t n = prims.size();
+  std::vector<double> pu(n), pv(n), rho(n);
+  double ulo = 1e300, uhi = -1e300, vlo = 1e300, vhi = -1e300, rhoSum = 0.0;
+  for (size_t i = 0; i < n; i++)
+  {
+    const HostObj * o = sph[prims[i].index];
+    const double C[3] = { (double)o->center[0], (double)o->center[1], (double)o->center[2] };
+    const double r = fabs((double)o->radius), m = (double)prims[i].m;
+    const double infl = r + m + 1.01 * sigma * (diag + r);
+    // distance from C backwards along l to the boundary of B inflated by infl (C is inside B)
+    double sMax = 1e300;
+    for (int k = 0; k < 3; k++)
+    {
+      const double dk = -l[k];
+      if (dk > 1e-300) sMax = std::min(sMax, (bhi[k] + infl - C[k]) / dk);
+      else if (dk < -1e-300) sMax = std::min(sMax, (blo[k] - infl - C[k]) / dk);
+    }
+    if (!(sMax < 1e300)) return false;
+    sMax = std::max(sMax, 0.0);
+    rho[i] = (r + m + sigma * sMax) * 1.001 + 1e-5 * diag + 1e-6 * (fabs(cb[0]) + fabs(cb[1]) + fabs(cb[2]));   // + the float evaluation of the cell coordinates
+    pu[i] = u[0] * C[0] + u[1] * C[1] + u[2] * C[2];
+    pv[i] = v[0] * C[0] + v[1] * C[1] + v[2] * C[2];
+    ulo = std::min(ulo, pu[i] - rho[i]); uhi = std::max(uhi, pu[i] + rho[i]);
+    vlo = std::min(vlo, pv[i] - rho[i]); vhi = std::max(vhi, pv[i] + rho[i]);
+    rhoSum += rho[i];
+  }
+  if (n == 0 || !(uhi > ulo) || !(vhi > vlo)) return false;
+  const double cell = std::max(std::max(uhi - ulo, vhi - vlo) / 256.0, 0.75 * rhoSum / (double)n);
+  const int nx = (int)std::min(256.0, ceil((uhi - ulo) / cell)) + 1, ny = (int)std::min(256.0, ceil((vhi - vlo) / cell)) + 1;
+  const double inv = 1.0 / cell;
+  std::vector<uint32_t> count((size_t)nx * ny + 1, 0);
+  auto cellsOf = [&](size_t i, int & x0, int & x1, int & y0, int & y1)
+  {
+    x0 = std::max(0, (int)floor((pu[i] - rho[i] - ulo) * inv)); x1 = std::min(nx - 1, (int)floor((pu[i] + rho[i] - ulo) * inv));
+    y0 = std::max(0, (int)floor((pv[i] - rho[i] - vlo) * inv)); y1 = std::min(ny - 1, (int)floor((pv[i] + rho[i] - vlo) * inv));
+  };
+  auto touches = [&](size_t i, int x, int y)     // the disc against the cell's square
+  {
+    const double cx0 = ulo + x * cell, cy0 = vlo + y * cell;
+    const double dx = std::max(std::max(cx0 - pu[i], pu[i] - (cx0 + cell)), 0.0), dy = std::max(std::max(cy0 - pv[i], pv[i] - (cy0 + cell)), 0.0);
+    return dx * dx + dy * dy <= rho[i] * rho[i];
+  };
+  for (int pass = 0; pass < 2; pass++)
+  {
+    if (pass == 1)
+    {
+      uint32_t run = 0;
+      for (size_t c = 0; c < (size_t)nx * ny; c++) { const uint32_t k = count[c]; count[c] = run; run += k; }
+      count[(size_t)nx * ny] = run;
+      out.cellStart = count;
+      out.spheres.resize(run); out.index.resize(run);
+    }
+    for (size_t i = 0; i < n; i++)
+    {
+      int x0, x1, y0, y1;
+      cellsOf(i, x0, x1, y0, y1);
+      for (int y = y0; y <= y1; y++)
+        for (int x = x0; x <= x1; x++)
+          if (touches(i, x, y))
+          {
+            const size_t c = (size_t)y * nx + x;
+            if (pass == 0) count[c]++;
+            else
+            {
+              const HostObj * o = sph[prims[i].index];
+              const uint32_t k = count[c]++;
+              out.spheres[k] = make_float4(o->center[0], o->center[1], o->center[2], o->sqRadius);
+              out.index[k] = prims[i].index;
+            }
+          }
+    }
+  }
+  LightGrid & g = out.g;
+  for (int k = 0; k < 3; k++) { g.u[k] = (float)(u[k] * inv); g.v[k] = (float)(v[k] * inv); }
+  g.u[3] = (float)(-ulo * inv); g.v[3] = (float)(-vlo * inv);
+  g.nx = nx; g.ny = ny;
+  g.cellStart = nullptr; g.itemSphere = nullptr; g.itemIndex = nullptr;
+  return true;
+}
+
 int uploadScene(rfx_ctx * ctx, cudaStream_t st)
 {
   if (!ctx->sceneDirty) return RFX_OK;
@@ -289,6 +416,8 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
   h.bvhPairs = nullptr;
   h.bvhRoot = 0;
   h.bvhFloat4 = 0;
+  h.lightGrids = nullptr;
+  ctx->lightGridsBuilt = 0;
   ctx->bvhDepth = 0;
   ctx->bvhFloat4 = 0;
   // automatic mode: more than 32 spheres, and no planes — a drop point on an (unbounded) plane can lie anywhere, so the box margins
@@ -409,6 +538,72 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
       h.bvhFloat4 = (uint32_t)((nLeaves + nInner) * 4);
       ctx->bvhFloat4 = h.bvhFloat4;
       h.bvhRoot = ref[0];
+
+      // shadow-ray candidate grids of the far lights (buildLightGrid).  B: the box of every drop point — all objects (planes are
+      // excluded by wantBvh's automatic mode; with planes present no grid is built), padded for the rounding of a drop point
+      ctx->lightGridsBuilt = 0;
+      if (ctx->lightGridsOn && pla.empty() && !ctx->lights.empty())
+      {
+        double blo[3] = { 1e300, 1e300, 1e300 }, bhi[3] = { -1e300, -1e300, -1e300 };
+        for (size_t i = 0; i < sph.size(); i++)
+          for (int k = 0; k < 3; k++)
+          {
+            blo[k] = std::min(blo[k], (double)sph[i]->center[k] - fabs((double)sph[i]->radius));
+            bhi[k] = std::max(bhi[k], (double)sph[i]->center[k] + fabs((double)sph[i]->radius));
+          }
+        for (const HostObj * t : tri)
+          for (int v = 0; v < 3; v++)
+            for (int k = 0; k < 3; k++)
+            {
+              blo[k] = std::min(blo[k], (double)t->triVerts[3 * v + k]);
+              bhi[k] = std::max(bhi[k], (double)t->triVerts[3 * v + k]);
+            }
+        {
+          const double ex = bhi[0] - blo[0], ey = bhi[1] - blo[1], ez = bhi[2] - blo[2];
+          const double pad = 1e-3 * sqrt(ex * ex + ey * ey + ez * ez) + 1e-5 * (fabs(blo[0]) + fabs(blo[1]) + fabs(blo[2]) + fabs(bhi[0]) + fabs(bhi[1]) + fabs(bhi[2]));
+          for (int k = 0; k < 3; k++) { blo[k] -= pad; bhi[k] += pad; }
+        }
+        std::vector<LightGrid> grids(ctx->lights.size());
+        std::vector<uint32_t> cells;
+        std::vector<float4> gsph;
+        std::vector<int> gidx;
+        std::vector<size_t> cellOff(ctx->lights.size(), 0), itemOff(ctx->lights.size(), 0);
+        for (size_t li = 0; li < ctx->lights.size(); li++)
+        {
+          LightGridHost lg;
+          memset(&grids[li], 0, sizeof(LightGrid));
+          if (!buildLightGrid(ctx->lights[li], sph, prims, blo, bhi, lg)) continue;
+          grids[li] = lg.g;
+          grids[li].nx = lg.g.nx; grids[li].ny = lg.g.ny;
+          cellOff[li] = cells.size(); itemOff[li] = gsph.size();
+          cells.insert(cells.end(), lg.cellStart.begin(), lg.cellStart.end());
+          gsph.insert(gsph.end(), lg.spheres.begin(), lg.spheres.end());
+          gidx.insert(gidx.end(), lg.index.begin(), lg.index.end());
+          grids[li].cellStart = reinterpret_cast<const uint32_t *>(1);    // marks "built": patched below once the arrays have their address
+          ctx->lightGridsBuilt++;
+        }
+        if (ctx->lightGridsBuilt)
+        {
+          if ((rc = ensure(ctx, ctx->dLightGrids, ctx->lightGridsCap, grids.size())) != RFX_OK) return rc;
+          if ((rc = ensure(ctx, ctx->dGridCells, ctx->gridCellsCap, cells.size())) != RFX_OK) return rc;
+          if ((rc = ensure(ctx, ctx->dGridSpheres, ctx->gridSpheresCap, std::max<size_t>(gsph.size(), 1))) != RFX_OK) return rc;
+          if ((rc = ensure(ctx, ctx->dGridIndex, ctx->gridIndexCap, std::max<size_t>(gidx.size(), 1))) != RFX_OK) return rc;
+          for (size_t li = 0; li < grids.size(); li++)
+            if (grids[li].cellStart)
+            {
+              grids[li].cellStart = ctx->dGridCells + cellOff[li];
+              grids[li].itemSphere = ctx->dGridSpheres + itemOff[li];   // cellStart offsets are relative to the light's own items
+              grids[li].itemIndex = ctx->dGridIndex + itemOff[li];
+            }
+          CK(cudaMemcpyAsync(ctx->dLightGrids, grids.data(), grids.size() * sizeof(LightGrid), cudaMemcpyHostToDevice, st));
+          CK(cudaMemcpyAsync(ctx->dGridCells, cells.data(), cells.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+          if (!gsph.empty()) CK(cudaMemcpyAsync(ctx->dGridSpheres, gsph.data(), gsph.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+          if (!gidx.empty()) CK(cudaMemcpyAsync(ctx->dGridIndex, gidx.data(), gidx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+          CK(cudaStreamSynchronize(st));
+          ctx->stats.h2d_bytes += grids.size() * sizeof(LightGrid) + cells.size() * 4 + gsph.size() * 16 + gidx.size() * 4;
+          h.lightGrids = ctx->dLightGrids;
+        }
+      }
     }
   }
   if (off > 200 * 1024) return fail(ctx, RFX_ERR_ARG, "scene too large for the shared-memory resident layout (200 KB)");
@@ -742,7 +937,7 @@ void rfx_destroy(rfx_ctx * ctx)
   for (HostTex & t : ctx->tex) if (t.dev) cudaFree(t.dev);
   cudaFree(ctx->dBlob); cudaFree(ctx->dLut); cudaFree(ctx->dImage); cudaFree(ctx->dSig); cudaFree(ctx->dRng);
   cudaFree(ctx->dRngPrefix); cudaFree(ctx->dRngLocate); cudaFree(ctx->dSampleStates); cudaFree(ctx->dStatus);
-  cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dBvhNodes); cudaFree(ctx->dBvhPrims); cudaFree(ctx->dTileLists[0]); cudaFree(ctx->dTileLists[1]); cudaFree(ctx->dTileCounts);
+  cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dBvhNodes); cudaFree(ctx->dBvhPrims); cudaFree(ctx->dLightGrids); cudaFree(ctx->dGridCells); cudaFree(ctx->dGridSpheres); cudaFree(ctx->dGridIndex); cudaFree(ctx->dTileLists[0]); cudaFree(ctx->dTileLists[1]); cudaFree(ctx->dTileCounts);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   cudaFree(ctx->dResolve); cudaFree(ctx->dQueue); cudaFree(ctx->dQueueCtl); cudaFree(ctx->dOwnBlocks);
   for (int i = 0; i < rfx_ctx::FRAME_SLOTS; i++)
@@ -1494,6 +1689,7 @@ int rfx_get_stats(rfx_ctx * ctx, rfx_stats * out)
     ctx->stats.trace_kernels++;
   }
   ctx->evUsed = 0;
+  ctx->stats.light_grids = (uint64_t)ctx->lightGridsBuilt;
   *out = ctx->stats;
   return RFX_OK;
 }
@@ -1539,6 +1735,13 @@ int rfx_set_option(rfx_ctx * ctx, const char * name, int64_t value)
   {
     if (value < 1) return fail(ctx, RFX_ERR_ARG, "rfx_set_option: max_calls_per_launch must be >= 1");
     ctx->maxCallsPerLaunch = (uint64_t)value;
+    return RFX_OK;
+  }
+  if (!strcmp(name, "light_grids"))
+  {
+    if (value != 0 && value != 1) return fail(ctx, RFX_ERR_ARG, "rfx_set_option: light_grids must be 0 or 1");
+    if (ctx->lightGridsOn != (value != 0)) ctx->sceneDirty = true;
+    ctx->lightGridsOn = value != 0;
     return RFX_OK;
   }
   if (!strcmp(name, "blob_wavefront"))

@@ -15,6 +15,9 @@
 //     stack in shared memory (one column per thread); "while-while" order — every lane walks to its next leaf, then the warp
 //     tests its leaves together.  A leaf is four contiguous sphere records (NaN-padded) tested behind one gate, like a quad of
 //     the constant-bank kernel.  The slab test is the one piece of arithmetic here that is not the reference's, so it is fused.
+//   * Shadow queries towards a FAR light do not walk the hierarchy: their rays are nearly parallel, so the host bins the spheres'
+//     (inflated) shadows on a plane across the light's direction and the query tests the candidate list of its origin's cell with
+//     the exact arithmetic (LightGrid, rfx_capi.cu buildLightGrid) — an any-hit query only asks whether something is hit.
 //   * 4x8 pixel tiles per warp on a 2-D grid, 128-bit framebuffer stores, 64 registers / 8 CTAs per SM.
 // Each step was measured (profiles/README.md: 6.66 -> 3.80 ms for a 3840x2160 frame of the 1024-sphere scene at depth 8).
 //
@@ -35,6 +38,11 @@ namespace
 #define RFX_QUEUE_RESERVE 1  // queue-driven kernel: consecutive records a lane reserves per atomic (1 measured best: the lanes of a warp
 #endif                       // then hold neighbouring paths; 4: +7 %, 8: +14 %; handing records out from a per-warp shared-memory
                              // buffer behind a __syncwarp per query: +11 % — profiles/r2_s6)
+#ifndef RFX_QUEUE_PHASES
+#define RFX_QUEUE_PHASES 1   // queue-driven kernel: a warp runs its pending shadow queries first (those lanes only), then a bounce trip for
+#endif                       // every lane: shadow trips are short (candidate grids), bounce trips run with all lanes in the hierarchy
+                             // (config 4 depth 8: 4.17 -> 3.84 ms with the grids, 4.20 -> 4.28 without; the same votes in the tile
+                             // kernels, whose lanes start together and alternate by themselves, cost 7 %: profiles/r2_grid)
 #ifndef RFX_BLOB_MINBLOCKS
 #define RFX_BLOB_MINBLOCKS 8
 #endif
@@ -95,8 +103,10 @@ __device__ __forceinline__ void consider(Hit & best, float dist, int idx, int or
 // All objects against one ray; `skip` = object the query ignores (-1 none); anyHit = shadow query (stop at the first hit).
 // STRIDE: threads of the CTA (the traversal stack is one column per thread).  SMEM: bvh points at the CTA's shared-memory copy of
 // the hierarchy (leaf sphere records, then pair nodes), else at the global arrays (read-only path).
+// grid: the candidate grid of the light this (shadow) query runs towards, NULL for bounce queries and for lights that have none.
 template <int STRIDE, bool SMEM>
-__device__ __forceinline__ void intersectBlob(const BlobView & sc, int * __restrict__ stack, V3 o, V3 d, int skip, bool anyHit, Hit & best)
+__device__ __forceinline__ void intersectBlob(const BlobView & sc, int * __restrict__ stack, V3 o, V3 d, int skip, bool anyHit, Hit & best,
+                                              const LightGrid * __restrict__ grid)
 {
   const SceneHeader & h = *sc.h;
   const float a = vsqlen(d);                                          // Sphere.cpp:50
@@ -162,6 +172,30 @@ __device__ __forceinline__ void intersectBlob(const BlobView & sc, int * __restr
       const float4 s = __ldg(&sc.spheres[i]);
       RFX_BLOB_REJECT(s, b, disc)
       if (RFX_BLOB_GATE(b, disc)) RFX_BLOB_TAIL(i, b, disc)
+    }
+  }
+  else if (grid != nullptr)
+  {
+    // Shadow query towards a far light: every sphere the ray can hit is listed in the cell of its origin (rfx_capi.cu,
+    // buildLightGrid); the query only asks WHETHER something is hit, so testing that list with the exact arithmetic gives the
+    // hierarchy walk's answer.  An origin outside the grid lies outside every sphere's (inflated) shadow.
+    const float fu = __fmaf_rn(grid->u[0], o.x, __fmaf_rn(grid->u[1], o.y, __fmaf_rn(grid->u[2], o.z, grid->u[3])));
+    const float fv = __fmaf_rn(grid->v[0], o.x, __fmaf_rn(grid->v[1], o.y, __fmaf_rn(grid->v[2], o.z, grid->v[3])));
+    const int cu = __float2int_rd(fu), cv = __float2int_rd(fv);
+    const int nx = grid->nx;
+    if ((unsigned)cu < (unsigned)nx && (unsigned)cv < (unsigned)grid->ny)
+    {
+      const uint32_t * cs = grid->cellStart + (cv * nx + cu);
+      uint32_t k = __ldg(cs);
+      const uint32_t e = __ldg(cs + 1);
+      const float4 * __restrict__ gs = grid->itemSphere;
+#pragma unroll 1
+      for (; k < e && open; k++)
+      {
+        const float4 s = __ldg(gs + k);
+        RFX_BLOB_REJECT(s, b, disc)
+        if (RFX_BLOB_GATE(b, disc)) RFX_BLOB_TAIL(__ldg(grid->itemIndex + k), b, disc)
+      }
     }
   }
   else
@@ -324,6 +358,7 @@ __device__ __forceinline__ bool traceBlob(const BlobView & sc, int * __restrict_
 {
   const SceneHeader & h = *sc.h;
   if (reflNumber <= 0) return true;
+  constexpr bool phased = RFX_QUEUE_PHASES != 0 && MODE == MODE_QUEUE;   // every lane of the warp is in this call and stays until all are done
 
   bool shadowQuery = false;
   int li = 0, hidx = -1;
@@ -332,14 +367,15 @@ __device__ __forceinline__ bool traceBlob(const BlobView & sc, int * __restrict_
   float rfs = 0.0f;          // continuation weight (Scene.cpp:196 / :207), negated for metals
   uint32_t rel = 0;          // MODE_QUEUE: pixel of the path in flight
   bool idle = MODE == MODE_QUEUE;
+  bool retired = false;      // phased queue mode: the queue is empty and this lane has no path; it keeps voting until its warp is done
 
   for (;;)
   {
-    if (MODE == MODE_QUEUE && idle)
+    if (MODE == MODE_QUEUE && idle && !retired)
     {
       // This lane's path has ended: take the next record.  A lane reserves RFX_QUEUE_RESERVE consecutive records at a time, and the
-      // idle lanes that arrive here together share one atomic.  Nothing forces the warp to reconverge here: lanes in short
-      // queries may loop ahead of lanes deep in a traversal (forcing them together with a __syncwarp per trip cost 19 %).
+      // idle lanes that arrive here together share one atomic.  (Before the candidate grids a shadow trip cost as much as a
+      // bounce trip and holding the warp together per trip cost 19 %; with them the votes below pay: see RFX_QUEUE_PHASES.)
       const uint32_t lane = threadIdx.x & 31u;
       if (feed->bufNext == feed->bufCount)
       {
@@ -353,7 +389,13 @@ __device__ __forceinline__ bool traceBlob(const BlobView & sc, int * __restrict_
         feed->bufCount = feed->bufNext + RFX_QUEUE_RESERVE;
       }
       const uint32_t idx = feed->bufNext++;
-      if (idx >= *feed->count) break;                                      // queue exhausted: this lane retires
+      if (idx >= *feed->count)                                             // queue exhausted: this lane retires
+      {
+        if (!phased) break;
+        retired = true;
+      }
+      else
+      {
       const uint4 * r = feed->records + 4 * (size_t)idx;
       const uint4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3];
       if (RFX_QUEUE_RESERVE > 1 && feed->bufNext != feed->bufCount) asm volatile("prefetch.global.L2 [%0];" :: "l"(r + 4));
@@ -366,11 +408,30 @@ __device__ __forceinline__ bool traceBlob(const BlobView & sc, int * __restrict_
       rngTriple(st, randDir.x, randDir.y, randDir.z);
       shadowQuery = false;
       idle = false;
+      }
+    }
+    if (phased)
+    {
+      // The trip's kind, decided by the warp: while any lane has a shadow query pending, those lanes run it and the others wait
+      // (a shadow query towards a far light tests a short candidate list); then every lane that holds a path runs its bounce
+      // query together.  Without this the lanes of a warp drift into both kinds (a queue-fed lane starts a path whenever its last
+      // one ends), and every trip pays the hierarchy walk of its bounce lanes plus the list walk of its shadow lanes.  The votes are
+      // also where the warp reconverges.  (Tile kernels: their lanes start together and alternate by themselves.)
+      const uint32_t alive = __ballot_sync(0xffffffffu, !retired);
+      if (alive == 0u) break;
+      const uint32_t wantShadow = __ballot_sync(0xffffffffu, !retired && shadowQuery);
+      if (retired || (wantShadow != 0u && !shadowQuery)) continue;
     }
 
     Hit hit;
     hit.dist = FLT_MAX; hit.idx = -1; hit.order = 0x7FFFFFFF; hit.t = 0; hit.u = 0; hit.v = 0;
-    intersectBlob<STRIDE, SMEM>(sc, stack, qo, qd, shadowQuery ? hidx : -1, shadowQuery, hit);
+    const LightGrid * grid = nullptr;
+    if (shadowQuery && h.lightGrids != nullptr)
+    {
+      grid = h.lightGrids + li;
+      if (grid->cellStart == nullptr) grid = nullptr;
+    }
+    intersectBlob<STRIDE, SMEM>(sc, stack, qo, qd, shadowQuery ? hidx : -1, shadowQuery, hit, grid);
 
     bool ended = false;
     if (!shadowQuery)

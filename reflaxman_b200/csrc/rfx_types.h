@@ -50,6 +50,18 @@ struct TexRef
   uint32_t w, h;
 };
 
+// Shadow-ray candidates of one far light (built by rfx_capi.cu next to the hierarchy, walked by rfx_trace_blob.cu).  Every shadow ray
+// towards the light is nearly parallel to the direction from the scene to the light, so the spheres it can hit are the ones whose
+// (inflated) shadow on a plane across that direction covers the ray's origin: a 2-D grid of candidate lists over that plane.
+struct LightGrid
+{
+  float u[4], v[4];                 // cell of a point p: column floor(u[0] p.x + u[1] p.y + u[2] p.z + u[3]), row likewise with v
+  int nx, ny;
+  const uint32_t * cellStart;       // [nx * ny + 1] offsets into the item arrays; NULL: no grid for this light (queries walk the hierarchy)
+  const float4 * itemSphere;        // candidate spheres (cx, cy, cz, r^2), cell after cell
+  const int * itemIndex;            // their positions in the sorted sphere array (materials, tie-break order, the skipped object)
+};
+
 struct SceneHeader
 {
   int nSpheres, nTris, nPlanes, nLights, nTextures;
@@ -65,6 +77,7 @@ struct SceneHeader
   int bvhRoot;                      // ref of the root (a pair node, or a leaf when there are <= 4 spheres)
   const float4 * bvhLeafSph;        // the same slots as (cx, cy, cz, r^2), NaN = unused: a leaf is 4 contiguous records
   uint32_t bvhFloat4;               // float4 count of [leaf records | pair nodes], contiguous from bvhLeafSph (what a CTA copies to shared memory)
+  const LightGrid * lightGrids;     // [nLights] when the hierarchy exists and some light is far enough for a grid, else NULL
 };
 
 // Small scenes travel as a kernel parameter (constant bank): see rfx_trace_small.cu

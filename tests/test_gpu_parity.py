@@ -559,3 +559,50 @@ def test_primary_cull_leaves_every_frame_identical(capi, which):
             assert np.array_equal(a.read_argb(), b.read_argb())
     finally:
         a.close(); b.close()
+
+
+def _with_lights(scene, lights):
+    out = dict(scene)
+    out["lights"] = lights
+    return out
+
+
+@pytest.mark.parametrize("case", ["far", "overhead", "grazing", "far+near", "near", "two_far"])
+def test_light_grid_equals_hierarchy_walk(capi, case):
+    """Scenes with a sphere hierarchy answer the shadow queries of far lights from a grid of candidate spheres across the light's
+    direction (rfx_capi.cu buildLightGrid) instead of walking the hierarchy.  The query is an any-hit query (Scene.cpp:131-143), so
+    a complete candidate list gives the same answer: frames, ray counts and the stream position are identical with the grids
+    on and off — far light (config 4's), straight overhead, grazing (long shadows), a far and a near light together (the near
+    one keeps the hierarchy), near light only (no grid), two far lights; tile kernel, wavefront pair and general kernel."""
+    far = ((11.8e9, 4.26e9, 3.08e9), 3.48e8, (1.0, 1.0, 0.95), 0.85)
+    lights = {
+        "far": [far],
+        "overhead": [((0.0, 5.0e6, 0.0), 2.0e5, (1.0, 0.9, 0.8), 0.9)],
+        "grazing": [((-4.0e5, 1.5e4, 2.0e5), 6.0e3, (0.9, 1.0, 1.0), 0.8)],
+        "far+near": [far, ((2.0, 6.0, -1.0), 0.5, (1.0, 0.6, 0.4), 0.6)],
+        "near": [((2.0, 6.0, -1.0), 0.5, (1.0, 0.6, 0.4), 0.6)],
+        "two_far": [far, ((-3.0e4, 2.0e4, -1.0e4), 9.0e2, (0.5, 0.6, 1.0), 0.5)],
+    }[case]
+    expect = {"far": 1, "overhead": 1, "grazing": 1, "far+near": 1, "near": 0, "two_far": 2}[case]
+    scene = _with_lights(S.synthetic_scene(16, floor=S.synthetic_texture(64, 64, 3)), lights)
+    W, H = 192, 108
+    cams = [S.default_camera(), S.camera_lookat((3.0, 0.8, 2.0), (-2.0, 0.2, -1.0), 1.3)]
+    results = {}
+    for on in (1, 0):
+        c = capi.Context(0)
+        try:
+            c.load_scene(scene); c.set_seeds(31, 31); c.set_image_size(W, H)
+            c.set_option("light_grids", on)
+            frames = [c.render_frames(cams, d) for d in (2, 8)]          # tile kernel (depth < 4) and wavefront pair
+            st = c.stats()
+            assert st["light_grids"] == (expect if on else 0), st
+            c.enable_signatures(True)                                      # general kernel
+            c.render(cams[1], 5)
+            results[on] = (frames, st["rays"], c.read_argb(), c.read_signatures(), c.get_seeds())
+        finally:
+            c.close()
+    for a, b in zip(results[1][0], results[0][0]):
+        assert np.array_equal(a, b)
+    assert results[1][1] == results[0][1]
+    assert np.array_equal(results[1][2], results[0][2]) and np.array_equal(results[1][3], results[0][3])
+    assert results[1][4] == results[0][4]
