@@ -807,6 +807,7 @@ int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, boo
       w.argbOut = argbOut;
       w.sigOut = ctx->sigOn ? ctx->dSig : nullptr;
       w.counters = ctx->dCounters;
+      w.lightGrids = ctx->lightGridsBuilt > 0;
       cudaEvent_t evA = nullptr, evB = nullptr;
       if (ctx->profiling)
       {
@@ -1326,6 +1327,7 @@ int rfx_render_strips(rfx_ctx * ctx, uint32_t strip_rows, uint32_t world, uint32
   w.fp.stripRows = strip_rows; w.fp.stripWorld = world; w.fp.stripRank = rank;
   w.sampleStates = ctx->dSampleStates;
   w.image = nullptr; w.argbOut = argb_device; w.sigOut = nullptr; w.counters = ctx->dCounters;
+  w.lightGrids = ctx->lightGridsBuilt > 0;
   cudaEvent_t evA = nullptr, evB = nullptr;
   if (ctx->profiling)
   {

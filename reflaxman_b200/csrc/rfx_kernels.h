@@ -85,6 +85,7 @@ struct TraceWork
   uint32_t * sigOut;            // optional per-pixel hit-path signature
   unsigned long long * counters;// device [32][2] striped {bounces, shadowRays}
   TileOrder order;              // fast constant-bank kernel only
+  bool lightGrids = false;      // blob scenes: the header carries candidate grids for some light (picks the kernel instantiation)
 };
 // blob scenes (rfx_trace_blob.cu).  launchTraceBlobFast: row-aligned slices (one sample per pixel, grid SSAA, additive jitter; ARGB
 // and/or float image out); one-sample ARGB slices run as a wavefront pair when queue scratch is given (persistentCtas: grid of
@@ -93,7 +94,10 @@ struct TraceWork
 // (BLOB_MAX_BVH_DEPTH): the traversal stack holds 24 entries per thread.
 constexpr int BLOB_MAX_BVH_DEPTH = 22;
 uint64_t blobWavePixels(const TraceWork & w);
-constexpr int BLOB_WAVE_MIN_DEPTH = 4;       // shallower reflection limits render with the single tile kernel (the wavefront gains from depth 4 on)
+#ifndef RFX_BLOB_WAVE_MIN_DEPTH
+#define RFX_BLOB_WAVE_MIN_DEPTH 3
+#endif
+constexpr int BLOB_WAVE_MIN_DEPTH = RFX_BLOB_WAVE_MIN_DEPTH;       // shallower reflection limits render with the single tile kernel (the wavefront gains from depth 3 on: 2.73 against 2.77 ms, profiles/r2_grid)
 // queueRecords: blobWavePixels(w) records of 64 bytes, queueCounters: 2 words
 int launchTraceBlobFast(const TraceWork & w, cudaStream_t st, void * queueRecords = nullptr, uint32_t * queueCounters = nullptr, uint32_t persistentCtas = 0,
                         int firstSegments = 2,    // segments the tile kernel renders before it queues a path (0: no wavefront)

@@ -38,11 +38,6 @@ namespace
 #define RFX_QUEUE_RESERVE 1  // queue-driven kernel: consecutive records a lane reserves per atomic (1 measured best: the lanes of a warp
 #endif                       // then hold neighbouring paths; 4: +7 %, 8: +14 %; handing records out from a per-warp shared-memory
                              // buffer behind a __syncwarp per query: +11 % — profiles/r2_s6)
-#ifndef RFX_QUEUE_PHASES
-#define RFX_QUEUE_PHASES 1   // queue-driven kernel: a warp runs its pending shadow queries first (those lanes only), then a bounce trip for
-#endif                       // every lane: shadow trips are short (candidate grids), bounce trips run with all lanes in the hierarchy
-                             // (config 4 depth 8: 4.17 -> 3.84 ms with the grids, 4.20 -> 4.28 without; the same votes in the tile
-                             // kernels, whose lanes start together and alternate by themselves, cost 7 %: profiles/r2_grid)
 #ifndef RFX_BLOB_MINBLOCKS
 #define RFX_BLOB_MINBLOCKS 8
 #endif
@@ -104,7 +99,8 @@ __device__ __forceinline__ void consider(Hit & best, float dist, int idx, int or
 // STRIDE: threads of the CTA (the traversal stack is one column per thread).  SMEM: bvh points at the CTA's shared-memory copy of
 // the hierarchy (leaf sphere records, then pair nodes), else at the global arrays (read-only path).
 // grid: the candidate grid of the light this (shadow) query runs towards, NULL for bounce queries and for lights that have none.
-template <int STRIDE, bool SMEM>
+// GRIDS = false compiles the grid branch out (the queue-driven kernel, see traceBlob).
+template <int STRIDE, bool SMEM, bool GRIDS>
 __device__ __forceinline__ void intersectBlob(const BlobView & sc, int * __restrict__ stack, V3 o, V3 d, int skip, bool anyHit, Hit & best,
                                               const LightGrid * __restrict__ grid)
 {
@@ -174,7 +170,7 @@ __device__ __forceinline__ void intersectBlob(const BlobView & sc, int * __restr
       if (RFX_BLOB_GATE(b, disc)) RFX_BLOB_TAIL(i, b, disc)
     }
   }
-  else if (grid != nullptr)
+  else if (GRIDS && grid != nullptr)
   {
     // Shadow query towards a far light: every sphere the ray can hit is listed in the cell of its origin (rfx_capi.cu,
     // buildLightGrid); the query only asks WHETHER something is hit, so testing that list with the exact arithmetic gives the
@@ -352,13 +348,19 @@ constexpr int MODE_QUEUE = 2;       // paths come from the queue; a lane whose p
 // (qo, qd) in: origin and ray of the path's next segment; mul, pix, events: Scene::trace's mulColor, pixelColor and the event
 // counter (bounce-loop iterations in the low half, shadow rays in the high half).  Returns true when the path has ended (pix is
 // final); MODE_FIRST returns false with (qo, qd, mul, pix, events) ready for the next segment.
-template <bool SIG, int MODE, int STRIDE = BLOB_THREADS, bool SMEM = false>
+// Candidate grids (GRIDS): the tile kernels' lanes alternate bounce and shadow queries together, so a shadow trip is a short list
+// walk for the whole warp (-12..16 % on the first two segments of config 4).  The queue-driven kernel's lanes are in both kinds of
+// query on every trip: a shadow lane rides along in the hierarchy walk of its warp's bounce lanes for free, and the list walk
+// would be added to the trip (+6 % measured; making the warp run its shadow lanes first and its bounce lanes together recovers
+// only part of it) — that kernel keeps walking the hierarchy for every query.  profiles/r2_grid has the measurements.
+// Kernels that serve the batch path are instantiated both ways and the host picks by scene, because the grid branch costs a scene
+// without far lights 4-5 % although it is never taken (registers across the walk).
+template <bool SIG, int MODE, int STRIDE = BLOB_THREADS, bool SMEM = false, bool GRIDS = (MODE != MODE_QUEUE)>
 __device__ __forceinline__ bool traceBlob(const BlobView & sc, int * __restrict__ stack, V3 & qo, V3 & qd, int reflNumber, V3 randDir,
                                           V3 & mul, V3 & pix, uint32_t & events, uint32_t & sig, QueueFeed * feed = nullptr, int firstSegments = 1)
 {
   const SceneHeader & h = *sc.h;
   if (reflNumber <= 0) return true;
-  constexpr bool phased = RFX_QUEUE_PHASES != 0 && MODE == MODE_QUEUE;   // every lane of the warp is in this call and stays until all are done
 
   bool shadowQuery = false;
   int li = 0, hidx = -1;
@@ -367,15 +369,14 @@ __device__ __forceinline__ bool traceBlob(const BlobView & sc, int * __restrict_
   float rfs = 0.0f;          // continuation weight (Scene.cpp:196 / :207), negated for metals
   uint32_t rel = 0;          // MODE_QUEUE: pixel of the path in flight
   bool idle = MODE == MODE_QUEUE;
-  bool retired = false;      // phased queue mode: the queue is empty and this lane has no path; it keeps voting until its warp is done
 
   for (;;)
   {
-    if (MODE == MODE_QUEUE && idle && !retired)
+    if (MODE == MODE_QUEUE && idle)
     {
       // This lane's path has ended: take the next record.  A lane reserves RFX_QUEUE_RESERVE consecutive records at a time, and the
-      // idle lanes that arrive here together share one atomic.  (Before the candidate grids a shadow trip cost as much as a
-      // bounce trip and holding the warp together per trip cost 19 %; with them the votes below pay: see RFX_QUEUE_PHASES.)
+      // idle lanes that arrive here together share one atomic.  Nothing forces the warp to reconverge here: lanes in short
+      // queries may loop ahead of lanes deep in a traversal (forcing them together with a __syncwarp per trip cost 19 %).
       const uint32_t lane = threadIdx.x & 31u;
       if (feed->bufNext == feed->bufCount)
       {
@@ -389,13 +390,7 @@ __device__ __forceinline__ bool traceBlob(const BlobView & sc, int * __restrict_
         feed->bufCount = feed->bufNext + RFX_QUEUE_RESERVE;
       }
       const uint32_t idx = feed->bufNext++;
-      if (idx >= *feed->count)                                             // queue exhausted: this lane retires
-      {
-        if (!phased) break;
-        retired = true;
-      }
-      else
-      {
+      if (idx >= *feed->count) break;                                      // queue exhausted: this lane retires
       const uint4 * r = feed->records + 4 * (size_t)idx;
       const uint4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3];
       if (RFX_QUEUE_RESERVE > 1 && feed->bufNext != feed->bufCount) asm volatile("prefetch.global.L2 [%0];" :: "l"(r + 4));
@@ -408,30 +403,16 @@ __device__ __forceinline__ bool traceBlob(const BlobView & sc, int * __restrict_
       rngTriple(st, randDir.x, randDir.y, randDir.z);
       shadowQuery = false;
       idle = false;
-      }
     }
-    if (phased)
-    {
-      // The trip's kind, decided by the warp: while any lane has a shadow query pending, those lanes run it and the others wait
-      // (a shadow query towards a far light tests a short candidate list); then every lane that holds a path runs its bounce
-      // query together.  Without this the lanes of a warp drift into both kinds (a queue-fed lane starts a path whenever its last
-      // one ends), and every trip pays the hierarchy walk of its bounce lanes plus the list walk of its shadow lanes.  The votes are
-      // also where the warp reconverges.  (Tile kernels: their lanes start together and alternate by themselves.)
-      const uint32_t alive = __ballot_sync(0xffffffffu, !retired);
-      if (alive == 0u) break;
-      const uint32_t wantShadow = __ballot_sync(0xffffffffu, !retired && shadowQuery);
-      if (retired || (wantShadow != 0u && !shadowQuery)) continue;
-    }
-
     Hit hit;
     hit.dist = FLT_MAX; hit.idx = -1; hit.order = 0x7FFFFFFF; hit.t = 0; hit.u = 0; hit.v = 0;
     const LightGrid * grid = nullptr;
-    if (shadowQuery && h.lightGrids != nullptr)
+    if (GRIDS && shadowQuery && h.lightGrids != nullptr)
     {
       grid = h.lightGrids + li;
       if (grid->cellStart == nullptr) grid = nullptr;
     }
-    intersectBlob<STRIDE, SMEM>(sc, stack, qo, qd, shadowQuery ? hidx : -1, shadowQuery, hit, grid);
+    intersectBlob<STRIDE, SMEM, GRIDS>(sc, stack, qo, qd, shadowQuery ? hidx : -1, shadowQuery, hit, grid);
 
     bool ended = false;
     if (!shadowQuery)
@@ -592,12 +573,12 @@ __device__ __forceinline__ bool traceBlob(const BlobView & sc, int * __restrict_
 }
 
 // one whole Scene::trace call
-template <bool SIG>
+template <bool SIG, bool GRIDS = true>
 __device__ __forceinline__ V3 tracePath(const BlobView & sc, int * __restrict__ stack, V3 origin, V3 ray, int reflNumber, V3 randDir, uint32_t & events, uint32_t & sig)
 {
   V3 qo = origin, qd = ray, mul = mk(1.0f, 1.0f, 1.0f), pix = mk(0.0f, 0.0f, 0.0f);
   events = 0;
-  traceBlob<SIG, MODE_PATH>(sc, stack, qo, qd, reflNumber, randDir, mul, pix, events, sig);
+  traceBlob<SIG, MODE_PATH, BLOB_THREADS, false, GRIDS>(sc, stack, qo, qd, reflNumber, randDir, mul, pix, events, sig);
   return pix;
 }
 
@@ -618,7 +599,7 @@ __device__ __forceinline__ void flushBlobCounters(unsigned long long * __restric
 // K2 for row-aligned slices of blob scenes.  MULTI = false: one sample per pixel, no jitter (the batch path of the bench).
 // MULTI = true: the same tiling for grid SSAA (Render.cpp:174-196: the thread walks its s*s samples in the reference's ssx, ssy
 // order so the sum is formed in the same order) and additive jitter / accumulation (Render.cpp:177-178, :196-207).
-template <bool MULTI>
+template <bool MULTI, bool GRIDS>
 __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob(const unsigned char * __restrict__ sceneBlob, const __grid_constant__ FrameParams fp,
                                                                 const uint32_t * __restrict__ sampleStates, uint32_t * __restrict__ argbOut,
                                                                 unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1,
@@ -647,7 +628,7 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
       V3 rd;
       rngTriple(s, rd.x, rd.y, rd.z);
       uint32_t events = 0, sig = 0;
-      c = tracePath<false>(sc, stackMem + threadIdx.x, eye, ray, fp.reflNum, rd, events, sig);   // one sample: colour / 1 == colour
+      c = tracePath<false, GRIDS>(sc, stackMem + threadIdx.x, eye, ray, fp.reflNum, rd, events, sig);   // one sample: colour / 1 == colour
       nBounces = events & 0xFFFFu; nShadow = events >> 16;
     }
     else
@@ -676,7 +657,7 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
                           (px * fp.view[3] + py * fp.view[4]) + fp.rz * fp.view[5],
                           (px * fp.view[6] + py * fp.view[7]) + fp.rz * fp.view[8]);
         uint32_t events = 0, sig = 0;
-        const V3 one = tracePath<false>(sc, stackMem + threadIdx.x, eye, ray, fp.reflNum, rd, events, sig);
+        const V3 one = tracePath<false, GRIDS>(sc, stackMem + threadIdx.x, eye, ray, fp.reflNum, rd, events, sig);
         nBounces += events & 0xFFFFu; nShadow += events >> 16;
         c = vadd(c, one);
       }
@@ -724,6 +705,7 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
 // queue-driven kernel, and what bounds both is SIMT divergence inside the traversal — the queue-driven kernel issues at
 // 11.5 of 32 lanes although every lane holds a path (ncu, profiles/r2_s7) — not idle lanes and not the L1 pipeline (the
 // shared-memory copy of the hierarchy is worth 1.5 %).
+template <bool GRIDS>
 __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_blob_wave_first(const unsigned char * __restrict__ sceneBlob, const __grid_constant__ FrameParams fp,
                                                                      const uint32_t * __restrict__ sampleStates, uint32_t * __restrict__ argbOut,
                                                                      unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1, PathQueue queue,
@@ -752,7 +734,7 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_blob_wave_
     V3 rd;
     rngTriple(s, rd.x, rd.y, rd.z);
     uint32_t sig = 0;
-    alive = !traceBlob<false, MODE_FIRST>(sc, stackMem + threadIdx.x, qo, qd, fp.reflNum, rd, mul, pix, events, sig, nullptr, firstSegments);
+    alive = !traceBlob<false, MODE_FIRST, BLOB_THREADS, false, GRIDS>(sc, stackMem + threadIdx.x, qo, qd, fp.reflNum, rd, mul, pix, events, sig, nullptr, firstSegments);
     if (!alive)
     {
       argbOut[q] = packArgb(pix.x, pix.y, pix.z);
@@ -976,7 +958,8 @@ int launchTraceBlobFast(const TraceWork & w, cudaStream_t st, void * queueRecord
     if (cudaMemsetAsync(queueCounters, 0, 2 * sizeof(uint32_t), st) != cudaSuccess) return 0;
     PathQueue q;
     q.records = reinterpret_cast<uint4 *>(queueRecords); q.count = queueCounters; q.cursor = queueCounters + 1;
-    k_blob_wave_first<<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, q, firstSegments);
+    if (w.lightGrids) k_blob_wave_first<true><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, q, firstSegments);
+    else k_blob_wave_first<false><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, q, firstSegments);
     // the hierarchy in shared memory when it fits next to the stacks of two 512-thread CTAs per SM
     const size_t stackBytes512 = (size_t)BLOB_STACK * 512 * sizeof(int), bvhBytes = (size_t)bvhFloat4 * sizeof(float4);
     if (bvhFloat4 && stackBytes512 + bvhBytes <= 100 * 1024)
@@ -990,8 +973,13 @@ int launchTraceBlobFast(const TraceWork & w, cudaStream_t st, void * queueRecord
   }
   // 128-bit framebuffer stores need a 16-byte aligned frame: a caller's offset sub-buffer goes to the general kernel
   if (w.argbOut && (fp.W & 3u) == 0u && (reinterpret_cast<uintptr_t>(w.argbOut) & 15u) != 0u) return 0;
-  if (fp.sampleNum == 1 && !fp.jitter) k_trace_blob<false><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.image);
-  else k_trace_blob<true><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.image);
+  const bool multi = !(fp.sampleNum == 1 && !fp.jitter);
+#define RFX_LAUNCH_BLOB(M, G) k_trace_blob<M, G><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.image)
+  if (!multi && w.lightGrids) RFX_LAUNCH_BLOB(false, true);
+  else if (!multi) RFX_LAUNCH_BLOB(false, false);
+  else if (w.lightGrids) RFX_LAUNCH_BLOB(true, true);
+  else RFX_LAUNCH_BLOB(true, false);
+#undef RFX_LAUNCH_BLOB
   return 1;
 }
 

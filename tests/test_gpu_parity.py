@@ -593,7 +593,7 @@ def test_light_grid_equals_hierarchy_walk(capi, case):
         try:
             c.load_scene(scene); c.set_seeds(31, 31); c.set_image_size(W, H)
             c.set_option("light_grids", on)
-            frames = [c.render_frames(cams, d) for d in (2, 8)]          # tile kernel (depth < 4) and wavefront pair
+            frames = [c.render_frames(cams, d) for d in (2, 8)]          # tile kernel (depth < 3) and wavefront pair
             st = c.stats()
             assert st["light_grids"] == (expect if on else 0), st
             c.enable_signatures(True)                                      # general kernel
@@ -606,3 +606,44 @@ def test_light_grid_equals_hierarchy_walk(capi, case):
     assert results[1][1] == results[0][1]
     assert np.array_equal(results[1][2], results[0][2]) and np.array_equal(results[1][3], results[0][3])
     assert results[1][4] == results[0][4]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_light_grid_random_scenes(capi, seed):
+    """Random sphere clouds (stacked, radii over two orders of magnitude, some overlapping) under one to three far lights from random
+    directions — from below, along an axis, nearly horizontal — plus a floor: grids on and off give identical frames and ray counts."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(40, 200))
+    objs = []
+    for i in range(n):
+        r = float(10 ** rng.uniform(-1.7, 0.2))
+        c = rng.uniform([-8, 0, -6], [8, 5, 6])
+        objs.append(("sphere", (float(c[0]), float(c[1]) + r, float(c[2])), r, int(i % 2), tuple(float(v) for v in rng.uniform(0.3, 1.0, 3)),
+                     float(rng.uniform(0.0, 1.0)), 0.0))
+    objs.append(("tri", (-14.0, 0.0, -10.0, -14.0, 0.0, 10.0, 14.0, 0.0, -10.0), S.MT_DIELECTRIC, (1.0, 1.0, 1.0), 0.9, 0.0, -1, (0.0, 0.0, 0.0, 1.0, 1.0, 0.0)))
+    objs.append(("tri", (-14.0, 0.0, 10.0, 14.0, 0.0, 10.0, 14.0, 0.0, -10.0), S.MT_DIELECTRIC, (1.0, 1.0, 1.0), 0.9, 0.0, -1, (0.0, 1.0, 1.0, 1.0, 1.0, 0.0)))
+    lights = []
+    for k in range(int(rng.integers(1, 4))):
+        d = rng.normal(size=3)
+        if seed % 4 == 1 and k == 0:
+            d = np.array([0.0, 1.0, 0.0])                       # along an axis
+        if seed % 4 == 2 and k == 0:
+            d = np.array([1.0, 0.02, 0.3])                      # nearly horizontal
+        d = d / np.linalg.norm(d)
+        dist = float(10 ** rng.uniform(3.0, 9.0))
+        lights.append((tuple(float(v) for v in d * dist), dist * float(rng.uniform(0.001, 0.04)), (1.0, 0.9, 0.8), float(rng.uniform(0.3, 0.9))))
+    scene = {"ambient": ((0.9, 0.9, 1.0), 0.2), "skybox": None, "textures": [], "lights": lights, "objects": objs}
+    cams = [S.default_camera(), S.camera_lookat(tuple(rng.uniform([-10, 0.5, -8], [10, 6, 8])), tuple(rng.uniform([-3, 0, -3], [3, 3, 3])), 1.2)]
+    res = {}
+    for on in (1, 0):
+        c = capi.Context(0)
+        try:
+            c.load_scene(scene); c.set_seeds(9, 9); c.set_image_size(128, 72)
+            c.set_bvh_mode(1)
+            c.set_option("light_grids", on)
+            res[on] = (c.render_frames(cams, 2), c.render_frames(cams, 6), c.stats())
+        finally:
+            c.close()
+    assert res[1][2]["light_grids"] == len(lights) and res[0][2]["light_grids"] == 0
+    assert np.array_equal(res[1][0], res[0][0]) and np.array_equal(res[1][1], res[0][1])
+    assert res[1][2]["rays"] == res[0][2]["rays"]
