@@ -153,6 +153,16 @@ struct rfx_ctx
   float4 * dGridSpheres = nullptr; size_t gridSpheresCap = 0;
   int * dGridIndex = nullptr; size_t gridIndexCap = 0;
   bool lightGridsOn = true;                 // rfx_set_option "light_grids"
+  // candidate spheres of the first query of a path per 32x32-pixel screen cell (EyeGrid, rfx_kernels.h), rebuilt when the camera,
+  // the image size or the scene changes
+  uint32_t * dEyeCells = nullptr; size_t eyeCellsCap = 0;
+  float4 * dEyeSpheres = nullptr; size_t eyeSpheresCap = 0;
+  int * dEyeIndex = nullptr; size_t eyeIndexCap = 0;
+  EyeGrid eyeGrid = { nullptr, nullptr, nullptr, 0, 0, 0 };
+  float eyeKey[16] = { 0 }; uint64_t eyeSceneKey = 0; bool eyeValid = false;
+  uint64_t sceneUploads = 0;                // bumped by uploadScene
+  bool eyeGridOn = true;                    // rfx_set_option "eye_grid"
+  uint64_t eyeGridBuilds = 0;
   int lightGridsBuilt = 0;                  // lights of the uploaded scene that have a grid
   int bvhMode = 0;                          // 0 auto (spheres > 32), 1 always, 2 never — tests compare both
 
@@ -367,6 +377,8 @@ bool buildLightGrid(const Light & L, const std::vector<const HostObj *> & sph, c
 int uploadScene(rfx_ctx * ctx, cudaStream_t st)
 {
   if (!ctx->sceneDirty) return RFX_OK;
+  ctx->sceneUploads++;
+  ctx->eyeValid = false;
 
   for (HostTex & t : ctx->tex)
     if (!t.uploaded)
@@ -723,6 +735,83 @@ int rankSamples(rfx_ctx * ctx, uint64_t n, bool skipOnly, cudaStream_t st, uint6
 
 // Fills w.order for a fast-kernel launch and remembers what the launch will have recorded (see TileOrder).  History is
 // only reused by a launch over exactly the same grid; any other launch of the fast kernel starts a new history.
+// ---- candidates of the first query of a path (EyeGrid) ------------------------------------------------------------------------------
+// Scenes with a sphere hierarchy: every path starts at the eye, so the spheres its first query can hit are the ones whose primary-ray
+// screen bounds (primarySphereBounds: the rectangles the constant-bank kernel's tiles use, conservative against the float noise of
+// the exact test, SSAA sub-samples and jitter) cover its pixel.  The host bins the rectangles into 32x32-pixel cells per camera; a
+// 4x8 tile lies in one cell, so its 32 lanes walk the same short list instead of the hierarchy.  Closest hit over a complete
+// candidate list is the hierarchy walk's answer (ties go to the lower insertion index in both).
+int buildEyeGrid(rfx_ctx * ctx, const FrameParams & fp, cudaStream_t st)
+{
+  ctx->eyeGrid.cellStart = nullptr;
+  if (!ctx->eyeGridOn || ctx->bvhDepth <= 0) return RFX_OK;
+  float key[16];
+  memcpy(key, fp.eye, 12); memcpy(key + 3, fp.view, 36);
+  key[12] = fp.rz; key[13] = fp.wHalf; key[14] = fp.hHalf; key[15] = (float)fp.W * 65536.0f + (float)fp.H;
+  if (ctx->eyeValid && ctx->eyeSceneKey == ctx->sceneUploads && !memcmp(key, ctx->eyeKey, sizeof(key)))
+  {
+    ctx->eyeGrid.cellStart = ctx->dEyeCells;
+    return RFX_OK;
+  }
+  ctx->eyeValid = false;
+  const PrimaryCamera cam = makePrimaryCamera(fp);
+  if (!cam.ok || fp.W == 0 || fp.H == 0) return RFX_OK;
+  const int shift = 5;
+  const int nx = (int)((fp.W + 31u) >> shift), ny = (int)((fp.H + 31u) >> shift);
+  if ((uint64_t)nx * ny > (1u << 22)) return RFX_OK;
+  struct Span { int x0, x1, y0, y1; };
+  std::vector<Span> spans;
+  std::vector<const HostObj *> sph;
+  for (const HostObj & o : ctx->objs) if (o.kind == 0) sph.push_back(&o);
+  spans.resize(sph.size());
+  std::vector<uint32_t> cells((size_t)nx * ny + 1, 0);
+  for (size_t i = 0; i < sph.size(); i++)
+  {
+    const int4 r = primarySphereBounds(cam, make_float4(sph[i]->center[0], sph[i]->center[1], sph[i]->center[2], sph[i]->sqRadius));
+    Span sp = { 1, 0, 1, 0 };
+    if (r.x <= r.y && r.z <= r.w && r.y >= 0 && r.w >= 0 && r.x < (int)fp.W && r.z < (int)fp.H)
+    {
+      sp.x0 = std::max(r.x, 0) >> shift; sp.x1 = std::min(r.y, (int)fp.W - 1) >> shift;
+      sp.y0 = std::max(r.z, 0) >> shift; sp.y1 = std::min(r.w, (int)fp.H - 1) >> shift;
+      for (int y = sp.y0; y <= sp.y1; y++)
+        for (int x = sp.x0; x <= sp.x1; x++) cells[(size_t)y * nx + x]++;
+    }
+    spans[i] = sp;
+  }
+  uint32_t run = 0;
+  for (size_t c = 0; c < (size_t)nx * ny; c++) { const uint32_t k = cells[c]; cells[c] = run; run += k; }
+  cells[(size_t)nx * ny] = run;
+  std::vector<float4> items(std::max<uint32_t>(run, 1));
+  std::vector<int> index(std::max<uint32_t>(run, 1));
+  std::vector<uint32_t> fill(cells.begin(), cells.end() - 1);
+  for (size_t i = 0; i < sph.size(); i++)
+  {
+    const Span & sp = spans[i];
+    for (int y = sp.y0; y <= sp.y1; y++)
+      for (int x = sp.x0; x <= sp.x1; x++)
+      {
+        const uint32_t k = fill[(size_t)y * nx + x]++;
+        items[k] = make_float4(sph[i]->center[0], sph[i]->center[1], sph[i]->center[2], sph[i]->sqRadius);
+        index[k] = (int)i;
+      }
+  }
+  int rc;
+  if ((rc = ensure(ctx, ctx->dEyeCells, ctx->eyeCellsCap, cells.size())) != RFX_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dEyeSpheres, ctx->eyeSpheresCap, items.size())) != RFX_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dEyeIndex, ctx->eyeIndexCap, index.size())) != RFX_OK) return rc;
+  // pageable sources: each copy is staged before its call returns, and the copies are ordered on the stream behind the kernels of
+  // the previous frame that still read the old grid
+  CK(cudaMemcpyAsync(ctx->dEyeCells, cells.data(), cells.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->dEyeSpheres, items.data(), items.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->dEyeIndex, index.data(), index.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  ctx->stats.h2d_bytes += cells.size() * 4 + items.size() * 16 + index.size() * 4;
+  ctx->eyeGrid.cellStart = ctx->dEyeCells; ctx->eyeGrid.itemSphere = ctx->dEyeSpheres; ctx->eyeGrid.itemIndex = ctx->dEyeIndex;
+  ctx->eyeGrid.nx = nx; ctx->eyeGrid.ny = ny; ctx->eyeGrid.shift = shift;
+  memcpy(ctx->eyeKey, key, sizeof(key)); ctx->eyeSceneKey = ctx->sceneUploads; ctx->eyeValid = true;
+  ctx->eyeGridBuilds++;
+  return RFX_OK;
+}
+
 int armTileOrder(rfx_ctx * ctx, TraceWork & w, cudaStream_t st)
 {
   w.order = TileOrder();
@@ -833,6 +922,8 @@ int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, boo
           if ((rc = ensure(ctx, ctx->dQueue, ctx->queueCap, (size_t)wavePixels * 4)) != RFX_OK) return rc;   // 64-byte records
           if (!ctx->dQueueCtl) CK(cudaMalloc((void **)&ctx->dQueueCtl, 2 * sizeof(uint32_t)));
         }
+        if (ctx->forcePath != 3 && (rc = buildEyeGrid(ctx, w.fp, st)) != RFX_OK) return rc;
+        w.eyeGrid = ctx->eyeGrid;
         int nl = ctx->forcePath == 3 ? 0 : launchTraceBlobFast(w, st, wavePixels ? ctx->dQueue : nullptr, ctx->dQueueCtl, (uint32_t)ctx->prop.multiProcessorCount * 8u,
                                                                ctx->blobWavefront, ctx->blobSmemBvh ? ctx->bvhFloat4 : 0u);
         if (nl) ctx->stats.launches_blob_fast += nl;
@@ -938,7 +1029,7 @@ void rfx_destroy(rfx_ctx * ctx)
   for (HostTex & t : ctx->tex) if (t.dev) cudaFree(t.dev);
   cudaFree(ctx->dBlob); cudaFree(ctx->dLut); cudaFree(ctx->dImage); cudaFree(ctx->dSig); cudaFree(ctx->dRng);
   cudaFree(ctx->dRngPrefix); cudaFree(ctx->dRngLocate); cudaFree(ctx->dSampleStates); cudaFree(ctx->dStatus);
-  cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dBvhNodes); cudaFree(ctx->dBvhPrims); cudaFree(ctx->dLightGrids); cudaFree(ctx->dGridCells); cudaFree(ctx->dGridSpheres); cudaFree(ctx->dGridIndex); cudaFree(ctx->dTileLists[0]); cudaFree(ctx->dTileLists[1]); cudaFree(ctx->dTileCounts);
+  cudaFree(ctx->dCounters); cudaFree(ctx->dRays); cudaFree(ctx->dBvhNodes); cudaFree(ctx->dBvhPrims); cudaFree(ctx->dEyeCells); cudaFree(ctx->dEyeSpheres); cudaFree(ctx->dEyeIndex); cudaFree(ctx->dLightGrids); cudaFree(ctx->dGridCells); cudaFree(ctx->dGridSpheres); cudaFree(ctx->dGridIndex); cudaFree(ctx->dTileLists[0]); cudaFree(ctx->dTileLists[1]); cudaFree(ctx->dTileCounts);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   cudaFree(ctx->dResolve); cudaFree(ctx->dQueue); cudaFree(ctx->dQueueCtl); cudaFree(ctx->dOwnBlocks);
   for (int i = 0; i < rfx_ctx::FRAME_SLOTS; i++)
@@ -1744,6 +1835,13 @@ int rfx_set_option(rfx_ctx * ctx, const char * name, int64_t value)
     if (value != 0 && value != 1) return fail(ctx, RFX_ERR_ARG, "rfx_set_option: light_grids must be 0 or 1");
     if (ctx->lightGridsOn != (value != 0)) ctx->sceneDirty = true;
     ctx->lightGridsOn = value != 0;
+    return RFX_OK;
+  }
+  if (!strcmp(name, "eye_grid"))
+  {
+    if (value != 0 && value != 1) return fail(ctx, RFX_ERR_ARG, "rfx_set_option: eye_grid must be 0 or 1");
+    ctx->eyeGridOn = value != 0;
+    ctx->eyeValid = false;
     return RFX_OK;
   }
   if (!strcmp(name, "blob_wavefront"))

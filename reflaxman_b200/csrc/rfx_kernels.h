@@ -74,6 +74,16 @@ struct TileOrder
   uint32_t capacity = 0;
 };
 
+// Blob scenes: candidate spheres of the FIRST query of a path (origin = eye) per screen cell of 2^shift x 2^shift pixels, rebuilt by the
+// host for every camera from the primary-ray screen bounds of the spheres; cellStart == NULL: none (the query walks the hierarchy)
+struct EyeGrid
+{
+  const uint32_t * cellStart;   // [nx * ny + 1]
+  const float4 * itemSphere;    // (cx, cy, cz, r^2) per (cell, sphere)
+  const int * itemIndex;        // position in the sorted sphere array
+  int nx, ny, shift;
+};
+
 struct TraceWork
 {
   const void * sceneBlob;       // device scene blob (SceneHeader first)
@@ -86,6 +96,7 @@ struct TraceWork
   unsigned long long * counters;// device [32][2] striped {bounces, shadowRays}
   TileOrder order;              // fast constant-bank kernel only
   bool lightGrids = false;      // blob scenes: the header carries candidate grids for some light (picks the kernel instantiation)
+  EyeGrid eyeGrid = { nullptr, nullptr, nullptr, 0, 0, 0 };
 };
 // blob scenes (rfx_trace_blob.cu).  launchTraceBlobFast: row-aligned slices (one sample per pixel, grid SSAA, additive jitter; ARGB
 // and/or float image out); one-sample ARGB slices run as a wavefront pair when queue scratch is given (persistentCtas: grid of
@@ -118,6 +129,10 @@ struct PrimaryCull
   int4 rect[SMALL_MAX_SPHERES + SMALL_MAX_TRIS];   // x0, x1, y0, y1 (inclusive, frame pixels); x0 > x1: no pixel
 };
 PrimaryCull makePrimaryCull(const SmallScene & sc, const FrameParams & fp);
+// the same bounds one sphere at a time (blob scenes bin them into the screen grid of the first query, EyeGrid)
+struct PrimaryCamera { double c[3][3], eye[3], rz, wHalf, hHalf, W, H; bool ok; };   // ok = false: no bounds (camera not orthonormal): whole image
+PrimaryCamera makePrimaryCamera(const FrameParams & fp);
+int4 primarySphereBounds(const PrimaryCamera & cam, const float4 & sphere);   // x0, x1, y0, y1 inclusive; x0 > x1: no pixel
 
 // ---- K3: resolve (imagePixel + argb) ---------------------------------------------------------------------------
 int launchResolve(const float * image, uint64_t nPixels, int additiveCounter, float * rgbfOut, uint32_t * argbOut, cudaStream_t st);

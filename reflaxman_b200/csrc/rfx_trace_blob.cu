@@ -99,10 +99,11 @@ __device__ __forceinline__ void consider(Hit & best, float dist, int idx, int or
 // STRIDE: threads of the CTA (the traversal stack is one column per thread).  SMEM: bvh points at the CTA's shared-memory copy of
 // the hierarchy (leaf sphere records, then pair nodes), else at the global arrays (read-only path).
 // grid: the candidate grid of the light this (shadow) query runs towards, NULL for bounce queries and for lights that have none.
-// GRIDS = false compiles the grid branch out (the queue-driven kernel, see traceBlob).
+// GRIDS = false compiles the candidate-list branch out (the queue-driven kernel, see traceBlob).
 template <int STRIDE, bool SMEM, bool GRIDS>
 __device__ __forceinline__ void intersectBlob(const BlobView & sc, int * __restrict__ stack, V3 o, V3 d, int skip, bool anyHit, Hit & best,
-                                              const LightGrid * __restrict__ grid)
+                                              const uint32_t * __restrict__ cellStart, const float4 * __restrict__ itemSphere,
+                                              const int * __restrict__ itemIndex, int cell)
 {
   const SceneHeader & h = *sc.h;
   const float a = vsqlen(d);                                          // Sphere.cpp:50
@@ -170,27 +171,20 @@ __device__ __forceinline__ void intersectBlob(const BlobView & sc, int * __restr
       if (RFX_BLOB_GATE(b, disc)) RFX_BLOB_TAIL(i, b, disc)
     }
   }
-  else if (GRIDS && grid != nullptr)
+  else if (GRIDS && cellStart != nullptr)
   {
-    // Shadow query towards a far light: every sphere the ray can hit is listed in the cell of its origin (rfx_capi.cu,
-    // buildLightGrid); the query only asks WHETHER something is hit, so testing that list with the exact arithmetic gives the
-    // hierarchy walk's answer.  An origin outside the grid lies outside every sphere's (inflated) shadow.
-    const float fu = __fmaf_rn(grid->u[0], o.x, __fmaf_rn(grid->u[1], o.y, __fmaf_rn(grid->u[2], o.z, grid->u[3])));
-    const float fv = __fmaf_rn(grid->v[0], o.x, __fmaf_rn(grid->v[1], o.y, __fmaf_rn(grid->v[2], o.z, grid->v[3])));
-    const int cu = __float2int_rd(fu), cv = __float2int_rd(fv);
-    const int nx = grid->nx;
-    if ((unsigned)cu < (unsigned)nx && (unsigned)cv < (unsigned)grid->ny)
+    // The query comes with a candidate list — cell `cell` of a grid the host built (traceBlob says which) — that holds every
+    // sphere this ray can hit: the exact test over that list gives the hierarchy walk's answer.  cell < 0: no sphere can be hit.
+    if (cell >= 0)
     {
-      const uint32_t * cs = grid->cellStart + (cv * nx + cu);
-      uint32_t k = __ldg(cs);
-      const uint32_t e = __ldg(cs + 1);
-      const float4 * __restrict__ gs = grid->itemSphere;
+      uint32_t k = __ldg(cellStart + cell);
+      const uint32_t e = __ldg(cellStart + cell + 1);
 #pragma unroll 1
       for (; k < e && open; k++)
       {
-        const float4 s = __ldg(gs + k);
+        const float4 s = __ldg(itemSphere + k);
         RFX_BLOB_REJECT(s, b, disc)
-        if (RFX_BLOB_GATE(b, disc)) RFX_BLOB_TAIL(__ldg(grid->itemIndex + k), b, disc)
+        if (RFX_BLOB_GATE(b, disc)) RFX_BLOB_TAIL(__ldg(itemIndex + k), b, disc)
       }
     }
   }
@@ -357,7 +351,8 @@ constexpr int MODE_QUEUE = 2;       // paths come from the queue; a lane whose p
 // without far lights 4-5 % although it is never taken (registers across the walk).
 template <bool SIG, int MODE, int STRIDE = BLOB_THREADS, bool SMEM = false, bool GRIDS = (MODE != MODE_QUEUE)>
 __device__ __forceinline__ bool traceBlob(const BlobView & sc, int * __restrict__ stack, V3 & qo, V3 & qd, int reflNumber, V3 randDir,
-                                          V3 & mul, V3 & pix, uint32_t & events, uint32_t & sig, QueueFeed * feed = nullptr, int firstSegments = 1)
+                                          V3 & mul, V3 & pix, uint32_t & events, uint32_t & sig, QueueFeed * feed = nullptr, int firstSegments = 1,
+                                          const EyeGrid * eyeGrid = nullptr, int eyeCell = -1)   // candidates of the first query (origin = eye), or NULL
 {
   const SceneHeader & h = *sc.h;
   if (reflNumber <= 0) return true;
@@ -406,13 +401,35 @@ __device__ __forceinline__ bool traceBlob(const BlobView & sc, int * __restrict_
     }
     Hit hit;
     hit.dist = FLT_MAX; hit.idx = -1; hit.order = 0x7FFFFFFF; hit.t = 0; hit.u = 0; hit.v = 0;
-    const LightGrid * grid = nullptr;
-    if (GRIDS && shadowQuery && h.lightGrids != nullptr)
+    // Candidate lists.  A shadow query towards a far light: the cell of its origin in the light's grid (rfx_capi.cu, buildLightGrid;
+    // an origin outside the grid lies outside every sphere's inflated shadow).  The first query of a path: the screen cell of its
+    // pixel in the camera's grid (buildEyeGrid).  Everything else walks the hierarchy.
+    const uint32_t * cellStart = nullptr;
+    const float4 * itemSphere = nullptr;
+    const int * itemIndex = nullptr;
+    int cell = -1;
+    if (GRIDS && shadowQuery)
     {
-      grid = h.lightGrids + li;
-      if (grid->cellStart == nullptr) grid = nullptr;
+      if (h.lightGrids != nullptr)
+      {
+        const LightGrid * grid = h.lightGrids + li;
+        if (grid->cellStart != nullptr)
+        {
+          const float fu = __fmaf_rn(grid->u[0], qo.x, __fmaf_rn(grid->u[1], qo.y, __fmaf_rn(grid->u[2], qo.z, grid->u[3])));
+          const float fv = __fmaf_rn(grid->v[0], qo.x, __fmaf_rn(grid->v[1], qo.y, __fmaf_rn(grid->v[2], qo.z, grid->v[3])));
+          const int cu = __float2int_rd(fu), cv = __float2int_rd(fv);
+          const int nx = grid->nx;
+          cellStart = grid->cellStart; itemSphere = grid->itemSphere; itemIndex = grid->itemIndex;
+          if ((unsigned)cu < (unsigned)nx && (unsigned)cv < (unsigned)grid->ny) cell = cv * nx + cu;
+        }
+      }
     }
-    intersectBlob<STRIDE, SMEM, GRIDS>(sc, stack, qo, qd, shadowQuery ? hidx : -1, shadowQuery, hit, grid);
+    else if (GRIDS && MODE != MODE_QUEUE && eyeGrid != nullptr && events == 0u)
+    {
+      cellStart = eyeGrid->cellStart; itemSphere = eyeGrid->itemSphere; itemIndex = eyeGrid->itemIndex;
+      cell = eyeCell;
+    }
+    intersectBlob<STRIDE, SMEM, GRIDS>(sc, stack, qo, qd, shadowQuery ? hidx : -1, shadowQuery, hit, cellStart, itemSphere, itemIndex, cell);
 
     bool ended = false;
     if (!shadowQuery)
@@ -574,11 +591,12 @@ __device__ __forceinline__ bool traceBlob(const BlobView & sc, int * __restrict_
 
 // one whole Scene::trace call
 template <bool SIG, bool GRIDS = true>
-__device__ __forceinline__ V3 tracePath(const BlobView & sc, int * __restrict__ stack, V3 origin, V3 ray, int reflNumber, V3 randDir, uint32_t & events, uint32_t & sig)
+__device__ __forceinline__ V3 tracePath(const BlobView & sc, int * __restrict__ stack, V3 origin, V3 ray, int reflNumber, V3 randDir, uint32_t & events, uint32_t & sig,
+                                        const EyeGrid * eyeGrid = nullptr, int eyeCell = -1)
 {
   V3 qo = origin, qd = ray, mul = mk(1.0f, 1.0f, 1.0f), pix = mk(0.0f, 0.0f, 0.0f);
   events = 0;
-  traceBlob<SIG, MODE_PATH, BLOB_THREADS, false, GRIDS>(sc, stack, qo, qd, reflNumber, randDir, mul, pix, events, sig);
+  traceBlob<SIG, MODE_PATH, BLOB_THREADS, false, GRIDS>(sc, stack, qo, qd, reflNumber, randDir, mul, pix, events, sig, nullptr, 1, eyeGrid, eyeCell);
   return pix;
 }
 
@@ -603,7 +621,7 @@ template <bool MULTI, bool GRIDS>
 __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob(const unsigned char * __restrict__ sceneBlob, const __grid_constant__ FrameParams fp,
                                                                 const uint32_t * __restrict__ sampleStates, uint32_t * __restrict__ argbOut,
                                                                 unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1,
-                                                                float * __restrict__ image)
+                                                                float * __restrict__ image, const __grid_constant__ EyeGrid eyeGrid)
 {
   __shared__ int stackMem[BLOB_STACK * BLOB_THREADS];
   const BlobView sc = blobView(sceneBlob);
@@ -612,6 +630,8 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
   const uint32_t y = y0 + blockIdx.y * BLOB_TILE_H + (lane / BLOB_TILE_W);
   const bool valid = x < fp.W && y < y1;
   uint32_t nBounces = 0, nShadow = 0, packed = 0, qOut = 0;
+  const EyeGrid * eg = (GRIDS && eyeGrid.cellStart != nullptr) ? &eyeGrid : nullptr;
+  const int eyeCell = eg ? (int)((y >> eyeGrid.shift) * (uint32_t)eyeGrid.nx + (x >> eyeGrid.shift)) : -1;
   if (valid)
   {
     const uint32_t q = y * fp.W + x;
@@ -628,7 +648,7 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
       V3 rd;
       rngTriple(s, rd.x, rd.y, rd.z);
       uint32_t events = 0, sig = 0;
-      c = tracePath<false, GRIDS>(sc, stackMem + threadIdx.x, eye, ray, fp.reflNum, rd, events, sig);   // one sample: colour / 1 == colour
+      c = tracePath<false, GRIDS>(sc, stackMem + threadIdx.x, eye, ray, fp.reflNum, rd, events, sig, eg, eyeCell);   // one sample: colour / 1 == colour
       nBounces = events & 0xFFFFu; nShadow = events >> 16;
     }
     else
@@ -657,7 +677,7 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
                           (px * fp.view[3] + py * fp.view[4]) + fp.rz * fp.view[5],
                           (px * fp.view[6] + py * fp.view[7]) + fp.rz * fp.view[8]);
         uint32_t events = 0, sig = 0;
-        const V3 one = tracePath<false, GRIDS>(sc, stackMem + threadIdx.x, eye, ray, fp.reflNum, rd, events, sig);
+        const V3 one = tracePath<false, GRIDS>(sc, stackMem + threadIdx.x, eye, ray, fp.reflNum, rd, events, sig, eg, eyeCell);
         nBounces += events & 0xFFFFu; nShadow += events >> 16;
         c = vadd(c, one);
       }
@@ -709,7 +729,7 @@ template <bool GRIDS>
 __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_blob_wave_first(const unsigned char * __restrict__ sceneBlob, const __grid_constant__ FrameParams fp,
                                                                      const uint32_t * __restrict__ sampleStates, uint32_t * __restrict__ argbOut,
                                                                      unsigned long long * __restrict__ counters, uint32_t y0, uint32_t y1, PathQueue queue,
-                                                                     int firstSegments)
+                                                                     int firstSegments, const __grid_constant__ EyeGrid eyeGrid)
 {
   __shared__ int stackMem[BLOB_STACK * BLOB_THREADS];
   const BlobView sc = blobView(sceneBlob);
@@ -720,6 +740,8 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_blob_wave_
   uint32_t nBounces = 0, nShadow = 0, events = 0, rel = 0, state0 = 0;
   V3 qo = mk(fp.eye[0], fp.eye[1], fp.eye[2]), qd = qo, mul = mk(1.0f, 1.0f, 1.0f), pix = mk(0.0f, 0.0f, 0.0f);
   bool alive = false;
+  const EyeGrid * eg = (GRIDS && eyeGrid.cellStart != nullptr) ? &eyeGrid : nullptr;
+  const int eyeCell = eg ? (int)((y >> eyeGrid.shift) * (uint32_t)eyeGrid.nx + (x >> eyeGrid.shift)) : -1;
   if (valid)
   {
     const uint32_t q = y * fp.W + x;
@@ -734,7 +756,7 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_blob_wave_
     V3 rd;
     rngTriple(s, rd.x, rd.y, rd.z);
     uint32_t sig = 0;
-    alive = !traceBlob<false, MODE_FIRST, BLOB_THREADS, false, GRIDS>(sc, stackMem + threadIdx.x, qo, qd, fp.reflNum, rd, mul, pix, events, sig, nullptr, firstSegments);
+    alive = !traceBlob<false, MODE_FIRST, BLOB_THREADS, false, GRIDS>(sc, stackMem + threadIdx.x, qo, qd, fp.reflNum, rd, mul, pix, events, sig, nullptr, firstSegments, eg, eyeCell);
     if (!alive)
     {
       argbOut[q] = packArgb(pix.x, pix.y, pix.z);
@@ -958,8 +980,8 @@ int launchTraceBlobFast(const TraceWork & w, cudaStream_t st, void * queueRecord
     if (cudaMemsetAsync(queueCounters, 0, 2 * sizeof(uint32_t), st) != cudaSuccess) return 0;
     PathQueue q;
     q.records = reinterpret_cast<uint4 *>(queueRecords); q.count = queueCounters; q.cursor = queueCounters + 1;
-    if (w.lightGrids) k_blob_wave_first<true><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, q, firstSegments);
-    else k_blob_wave_first<false><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, q, firstSegments);
+    if (w.lightGrids || w.eyeGrid.cellStart != nullptr) k_blob_wave_first<true><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, q, firstSegments, w.eyeGrid);
+    else k_blob_wave_first<false><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, q, firstSegments, w.eyeGrid);
     // the hierarchy in shared memory when it fits next to the stacks of two 512-thread CTAs per SM
     const size_t stackBytes512 = (size_t)BLOB_STACK * 512 * sizeof(int), bvhBytes = (size_t)bvhFloat4 * sizeof(float4);
     if (bvhFloat4 && stackBytes512 + bvhBytes <= 100 * 1024)
@@ -974,10 +996,11 @@ int launchTraceBlobFast(const TraceWork & w, cudaStream_t st, void * queueRecord
   // 128-bit framebuffer stores need a 16-byte aligned frame: a caller's offset sub-buffer goes to the general kernel
   if (w.argbOut && (fp.W & 3u) == 0u && (reinterpret_cast<uintptr_t>(w.argbOut) & 15u) != 0u) return 0;
   const bool multi = !(fp.sampleNum == 1 && !fp.jitter);
-#define RFX_LAUNCH_BLOB(M, G) k_trace_blob<M, G><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.image)
-  if (!multi && w.lightGrids) RFX_LAUNCH_BLOB(false, true);
+#define RFX_LAUNCH_BLOB(M, G) k_trace_blob<M, G><<<grid, BLOB_THREADS, 0, st>>>(blob, fp, w.sampleStates, w.argbOut, w.counters, y0, y1, w.image, w.eyeGrid)
+  const bool grids = w.lightGrids || w.eyeGrid.cellStart != nullptr;
+  if (!multi && grids) RFX_LAUNCH_BLOB(false, true);
   else if (!multi) RFX_LAUNCH_BLOB(false, false);
-  else if (w.lightGrids) RFX_LAUNCH_BLOB(true, true);
+  else if (grids) RFX_LAUNCH_BLOB(true, true);
   else RFX_LAUNCH_BLOB(true, false);
 #undef RFX_LAUNCH_BLOB
   return 1;

@@ -571,25 +571,37 @@ static int4 cullTriangle(const double * c0, const double * c1, const double * c2
   return make_int4(cullClamp(floor(x0 - CULL_PIX_MARGIN)), cullClamp(ceil(x1 + CULL_PIX_MARGIN)), cullClamp(floor(y0 - CULL_PIX_MARGIN)), cullClamp(ceil(y1 + CULL_PIX_MARGIN)));
 }
 
+PrimaryCamera makePrimaryCamera(const FrameParams & fp)
+{
+  // ray = rx * c0 + ry * c1 + rz * c2 (Render.cpp:154-156): the bounds need an orthonormal camera (Camera.cpp:24-36 builds one)
+  PrimaryCamera cam;
+  for (int j = 0; j < 3; j++) { cam.eye[j] = (double)fp.eye[j]; for (int i = 0; i < 3; i++) cam.c[j][i] = (double)fp.view[3 * i + j]; }
+  cam.rz = (double)fp.rz; cam.wHalf = (double)fp.wHalf; cam.hHalf = (double)fp.hHalf; cam.W = (double)fp.W; cam.H = (double)fp.H;
+  cam.ok = fp.rz > 0.0f && fp.rz < 1e30f && fabs(cam.eye[0]) < 1e30 && fabs(cam.eye[1]) < 1e30 && fabs(cam.eye[2]) < 1e30;
+  for (int a = 0; a < 3 && cam.ok; a++)
+    for (int b = 0; b < 3; b++)
+    {
+      const double dot = cam.c[a][0] * cam.c[b][0] + cam.c[a][1] * cam.c[b][1] + cam.c[a][2] * cam.c[b][2];
+      if (!(fabs(dot - (a == b ? 1.0 : 0.0)) < 1e-4)) cam.ok = false;
+    }
+  return cam;
+}
+
+int4 primarySphereBounds(const PrimaryCamera & cam, const float4 & sphere)
+{
+  if (!cam.ok) return cullFull();
+  return cullSphere(cam.c[0], cam.c[1], cam.c[2], cam.eye, cam.rz, cam.wHalf, cam.hHalf, sphere);
+}
+
 PrimaryCull makePrimaryCull(const SmallScene & sc, const FrameParams & fp)
 {
   PrimaryCull pc;
   for (int i = 0; i < SMALL_MAX_SPHERES + SMALL_MAX_TRIS; i++) pc.rect[i] = cullFull();
-  // ray = rx * c0 + ry * c1 + rz * c2 (Render.cpp:154-156): the bounds need an orthonormal camera (Camera.cpp:24-36 builds one)
-  double c[3][3], eye[3];
-  for (int j = 0; j < 3; j++) { eye[j] = (double)fp.eye[j]; for (int i = 0; i < 3; i++) c[j][i] = (double)fp.view[3 * i + j]; }
-  bool ok = fp.rz > 0.0f && fp.rz < 1e30f && fabs(eye[0]) < 1e30 && fabs(eye[1]) < 1e30 && fabs(eye[2]) < 1e30;
-  for (int a = 0; a < 3 && ok; a++)
-    for (int b = 0; b < 3; b++)
-    {
-      const double dot = c[a][0] * c[b][0] + c[a][1] * c[b][1] + c[a][2] * c[b][2];
-      if (!(fabs(dot - (a == b ? 1.0 : 0.0)) < 1e-4)) ok = false;
-    }
-  if (!ok) return pc;
-  for (int i = 0; i < sc.nS && i < SMALL_MAX_SPHERES; i++)
-    pc.rect[i] = cullSphere(c[0], c[1], c[2], eye, (double)fp.rz, (double)fp.wHalf, (double)fp.hHalf, sc.sph[i]);
+  const PrimaryCamera cam = makePrimaryCamera(fp);
+  if (!cam.ok) return pc;
+  for (int i = 0; i < sc.nS && i < SMALL_MAX_SPHERES; i++) pc.rect[i] = primarySphereBounds(cam, sc.sph[i]);
   for (int k = 0; k < sc.nT && k < SMALL_MAX_TRIS; k++)
-    pc.rect[SMALL_MAX_SPHERES + k] = cullTriangle(c[0], c[1], c[2], eye, (double)fp.rz, (double)fp.wHalf, (double)fp.hHalf, (double)fp.W, (double)fp.H, sc.tri[k]);
+    pc.rect[SMALL_MAX_SPHERES + k] = cullTriangle(cam.c[0], cam.c[1], cam.c[2], cam.eye, cam.rz, cam.wHalf, cam.hHalf, cam.W, cam.H, sc.tri[k]);
   return pc;
 }
 

@@ -647,3 +647,50 @@ def test_light_grid_random_scenes(capi, seed):
     assert res[1][2]["light_grids"] == len(lights) and res[0][2]["light_grids"] == 0
     assert np.array_equal(res[1][0], res[0][0]) and np.array_equal(res[1][1], res[0][1])
     assert res[1][2]["rays"] == res[0][2]["rays"]
+
+
+@pytest.mark.parametrize("which", ["grid16", "cloud"])
+def test_eye_grid_equals_hierarchy_walk(capi, which):
+    """Scenes with a sphere hierarchy take the candidates of a path's FIRST query (origin = eye) from a screen grid the host bins per
+    camera out of the spheres' primary-ray bounds (rfx_capi.cu buildEyeGrid) instead of walking the hierarchy.  Cameras all over the
+    place — orbit, inside spheres, under the floor, looking away, fov 0.3..2.6: frames, ray counts and stream positions are identical
+    with the grid on and off; tile kernel (depth 1 and 2), wavefront pair (depth 6) and 2x2 SSAA through the Render API."""
+    P = _primary_proto()
+    if which == "grid16":
+        scene = S.synthetic_scene(16, floor=S.synthetic_texture(64, 64, 3))
+    else:
+        rng = np.random.default_rng(77)
+        objs = []
+        for i in range(150):
+            r = float(10 ** rng.uniform(-1.5, 0.3))
+            c = rng.uniform([-8, 0, -6], [8, 5, 6])
+            objs.append(("sphere", (float(c[0]), float(c[1]) + r, float(c[2])), r, int(i % 2), tuple(float(v) for v in rng.uniform(0.3, 1.0, 3)),
+                         float(rng.uniform(0.0, 1.0)), 0.0))
+        objs.append(("tri", (-14.0, 0.0, -10.0, -14.0, 0.0, 10.0, 14.0, 0.0, -10.0), S.MT_DIELECTRIC, (1.0, 1.0, 1.0), 0.9, 0.0, -1, (0.0, 0.0, 0.0, 1.0, 1.0, 0.0)))
+        objs.append(("tri", (-14.0, 0.0, 10.0, 14.0, 0.0, 10.0, 14.0, 0.0, -10.0), S.MT_DIELECTRIC, (1.0, 1.0, 1.0), 0.9, 0.0, -1, (0.0, 1.0, 1.0, 1.0, 1.0, 0.0)))
+        scene = {"ambient": ((0.9, 0.9, 1.0), 0.2), "skybox": None, "textures": [], "lights": S.default_scene()["lights"], "objects": objs}
+    sph, _ = P.scene_arrays(scene)
+    cams = P.random_cameras(30, 5, sph)
+    W, H = 200, 120
+    res = {}
+    for on in (1, 0):
+        c = capi.Context(0)
+        try:
+            c.load_scene(scene); c.set_seeds(3, 3); c.set_image_size(W, H)
+            c.set_bvh_mode(1)
+            c.set_option("eye_grid", on)
+            frames = [c.render_frames(cams, d) for d in (1, 2, 6)]
+            st = c.stats()
+            assert st["launches_blob_fast"] == len(cams) * 4 and st["launches_blob_any"] == 0, st
+            ss = []
+            for cam in cams[::6]:
+                c.render(cam, 4, samples=2)
+                ss.append(c.read_argb())
+            res[on] = (frames, st["rays"], ss, c.get_seeds())
+        finally:
+            c.close()
+    for a, b in zip(res[1][0], res[0][0]):
+        assert np.array_equal(a, b)
+    assert res[1][1] == res[0][1] and res[1][3] == res[0][3]
+    for a, b in zip(res[1][2], res[0][2]):
+        assert np.array_equal(a, b)

@@ -199,6 +199,8 @@ def config4(env, steps=5, brute=False, depths=(1, 2, 3, 4, 5, 6, 7, 8), fp32_pea
         ctx.set_option("blob_smem_bvh", int(os.environ["RFX_BLOB_SMEM_BVH"]))
     if os.environ.get("RFX_FORCE_PATH"):
         ctx.force_path(int(os.environ["RFX_FORCE_PATH"]))   # 3 = general blob kernel only (A/B against the batch kernel)
+    if os.environ.get("RFX_EYE_GRID"):
+        ctx.set_option("eye_grid", int(os.environ["RFX_EYE_GRID"]))         # 0 = first queries walk the hierarchy (A/B)
     if os.environ.get("RFX_LIGHT_GRIDS"):
         ctx.set_option("light_grids", int(os.environ["RFX_LIGHT_GRIDS"]))   # 0 = shadow queries walk the hierarchy (A/B)
     out = torch.empty((1, Hd, Wd), dtype=torch.int32, device="cuda")
