@@ -181,7 +181,9 @@ RFX_API int rfx_enable_profiling(rfx_ctx * ctx, int on);
  * kernel keeps a small sphere hierarchy in shared memory (default 1).  "tile_order_period": the cost-ordered tile scheduling of the
  * constant-bank fast kernel records the tiles' cost classes on every k-th launch over the same grid and replays the last recording
  * in between (default 8).  "light_grids": scenes with a sphere hierarchy answer the shadow queries of far lights from a 2-D grid of
- * candidate spheres across the light's direction instead of walking the hierarchy (default 1).  Frames are bit-identical under
+ * candidate spheres across the light's direction instead of walking the hierarchy (default 1).  "eye_grid": the same scenes take the
+ * candidates of a path's first query (origin = eye) from a screen grid binned per camera out of the spheres' primary-ray bounds
+ * (default 1).  Frames are bit-identical under
  * every setting. */
 RFX_API int rfx_set_option(rfx_ctx * ctx, const char * name, int64_t value);
 /* kernel selection: 0 = automatic (constant-bank kernels when the scene fits, the blob kernels otherwise),

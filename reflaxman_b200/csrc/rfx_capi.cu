@@ -159,7 +159,7 @@ struct rfx_ctx
   float4 * dEyeSpheres = nullptr; size_t eyeSpheresCap = 0;
   int * dEyeIndex = nullptr; size_t eyeIndexCap = 0;
   EyeGrid eyeGrid = { nullptr, nullptr, nullptr, 0, 0, 0 };
-  float eyeKey[16] = { 0 }; uint64_t eyeSceneKey = 0; bool eyeValid = false;
+  uint32_t eyeKey[17] = { 0 }; uint64_t eyeSceneKey = 0; bool eyeValid = false;   // camera (eye, view, rz, wHalf, hHalf as bits) + W, H
   uint64_t sceneUploads = 0;                // bumped by uploadScene
   bool eyeGridOn = true;                    // rfx_set_option "eye_grid"
   uint64_t eyeGridBuilds = 0;
@@ -745,9 +745,10 @@ int buildEyeGrid(rfx_ctx * ctx, const FrameParams & fp, cudaStream_t st)
 {
   ctx->eyeGrid.cellStart = nullptr;
   if (!ctx->eyeGridOn || ctx->bvhDepth <= 0) return RFX_OK;
-  float key[16];
+  uint32_t key[17];
   memcpy(key, fp.eye, 12); memcpy(key + 3, fp.view, 36);
-  key[12] = fp.rz; key[13] = fp.wHalf; key[14] = fp.hHalf; key[15] = (float)fp.W * 65536.0f + (float)fp.H;
+  memcpy(key + 12, &fp.rz, 4); memcpy(key + 13, &fp.wHalf, 4); memcpy(key + 14, &fp.hHalf, 4);
+  key[15] = fp.W; key[16] = fp.H;
   if (ctx->eyeValid && ctx->eyeSceneKey == ctx->sceneUploads && !memcmp(key, ctx->eyeKey, sizeof(key)))
   {
     ctx->eyeGrid.cellStart = ctx->dEyeCells;
@@ -922,7 +923,7 @@ int renderRange(rfx_ctx * ctx, uint64_t p0, uint64_t p1, uint32_t * argbOut, boo
           if ((rc = ensure(ctx, ctx->dQueue, ctx->queueCap, (size_t)wavePixels * 4)) != RFX_OK) return rc;   // 64-byte records
           if (!ctx->dQueueCtl) CK(cudaMalloc((void **)&ctx->dQueueCtl, 2 * sizeof(uint32_t)));
         }
-        if (ctx->forcePath != 3 && (rc = buildEyeGrid(ctx, w.fp, st)) != RFX_OK) return rc;
+        if ((rc = buildEyeGrid(ctx, w.fp, st)) != RFX_OK) return rc;
         w.eyeGrid = ctx->eyeGrid;
         int nl = ctx->forcePath == 3 ? 0 : launchTraceBlobFast(w, st, wavePixels ? ctx->dQueue : nullptr, ctx->dQueueCtl, (uint32_t)ctx->prop.multiProcessorCount * 8u,
                                                                ctx->blobWavefront, ctx->blobSmemBvh ? ctx->bvhFloat4 : 0u);

@@ -820,13 +820,15 @@ __global__ void __launch_bounds__(THREADS, SMEM ? 2 : RFX_BLOB_MINBLOCKS) k_blob
 __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob_any(const unsigned char * __restrict__ sceneBlob, const __grid_constant__ FrameParams fp,
                                                                     const uint32_t * __restrict__ sampleStates, float * __restrict__ image,
                                                                     uint32_t * __restrict__ argbOut, uint32_t * __restrict__ sigOut,
-                                                                    unsigned long long * __restrict__ counters, int tiled)
+                                                                    unsigned long long * __restrict__ counters, int tiled,
+                                                                    const __grid_constant__ EyeGrid eyeGrid)
 {
   __shared__ int stackMem[BLOB_STACK * BLOB_THREADS];
   const BlobView sc = blobView(sceneBlob);
   uint32_t nBounces = 0, nShadow = 0;
   const V3 eye = mk(fp.eye[0], fp.eye[1], fp.eye[2]);
   const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const EyeGrid * eg = eyeGrid.cellStart != nullptr ? &eyeGrid : nullptr;
 
   // ---- which pixel does this lane own, and how many Scene::trace calls does it make
   const bool blockMode = fp.sampleNum < 0;                 // block preview, Render.cpp:158-173
@@ -877,6 +879,7 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
     }
     V3 fin = mk(0.0f, 0.0f, 0.0f);
     uint32_t sig = 2166136261u;
+    const int eyeCell = eg ? (int)((y >> eyeGrid.shift) * (uint32_t)eyeGrid.nx + (x >> eyeGrid.shift)) : -1;
     const uint32_t * st = sampleStates + firstState;
     const int nCalls = sn * sn;
     int ssx = 0, ssy = 0;
@@ -897,7 +900,7 @@ __global__ void __launch_bounds__(BLOB_THREADS, RFX_BLOB_MINBLOCKS) k_trace_blob
                         (px * fp.view[3] + py * fp.view[4]) + fp.rz * fp.view[5],
                         (px * fp.view[6] + py * fp.view[7]) + fp.rz * fp.view[8]);
       uint32_t events = 0;
-      const V3 c = tracePath<true>(sc, stackMem + threadIdx.x, eye, ray, fp.reflNum, rd, events, sig);
+      const V3 c = tracePath<true>(sc, stackMem + threadIdx.x, eye, ray, fp.reflNum, rd, events, sig, eg, eyeCell);
       nBounces += events & 0xFFFFu; nShadow += events >> 16;
       fin = blockMode ? c : vadd(fin, c);
       if (++ssy == sn) { ssy = 0; ssx++; }                  // ssx outer, ssy inner: the reference's summation order
@@ -1031,7 +1034,7 @@ int launchTraceBlobAny(const TraceWork & w, cudaStream_t st)
   if (nThreads == 0) return 0;
   const uint32_t blocks = (uint32_t)((nThreads + BLOB_THREADS - 1) / BLOB_THREADS);
   k_trace_blob_any<<<blocks, BLOB_THREADS, 0, st>>>(reinterpret_cast<const unsigned char *>(w.sceneBlob), fp, w.sampleStates, w.image, w.argbOut, w.sigOut,
-                                                    w.counters, tiled);
+                                                    w.counters, tiled, w.eyeGrid);
   return 1;
 }
 

@@ -654,7 +654,8 @@ def test_eye_grid_equals_hierarchy_walk(capi, which):
     """Scenes with a sphere hierarchy take the candidates of a path's FIRST query (origin = eye) from a screen grid the host bins per
     camera out of the spheres' primary-ray bounds (rfx_capi.cu buildEyeGrid) instead of walking the hierarchy.  Cameras all over the
     place — orbit, inside spheres, under the floor, looking away, fov 0.3..2.6: frames, ray counts and stream positions are identical
-    with the grid on and off; tile kernel (depth 1 and 2), wavefront pair (depth 6) and 2x2 SSAA through the Render API."""
+    with the grid on and off; tile kernel (depth 1 and 2), wavefront pair (depth 6), 2x2 SSAA through the Render API, and the general
+    kernel on ragged renderNext slices with identical hit-path signatures."""
     P = _primary_proto()
     if which == "grid16":
         scene = S.synthetic_scene(16, floor=S.synthetic_texture(64, 64, 3))
@@ -686,7 +687,13 @@ def test_eye_grid_equals_hierarchy_walk(capi, which):
             for cam in cams[::6]:
                 c.render(cam, 4, samples=2)
                 ss.append(c.read_argb())
-            res[on] = (frames, st["rays"], ss, c.get_seeds())
+            c.enable_signatures(True)                                      # general kernel (every renderNext mode), hit paths recorded
+            gen = []
+            for cam in cams[1::7]:
+                c.render(cam, 5, chunk=W * 7 + 13)                           # ragged renderNext slices
+                gen.append((c.read_argb(), c.read_signatures()))
+            assert c.stats()["launches_blob_any"] > 0
+            res[on] = (frames, st["rays"], ss, c.get_seeds(), gen)
         finally:
             c.close()
     for a, b in zip(res[1][0], res[0][0]):
@@ -694,3 +701,5 @@ def test_eye_grid_equals_hierarchy_walk(capi, which):
     assert res[1][1] == res[0][1] and res[1][3] == res[0][3]
     for a, b in zip(res[1][2], res[0][2]):
         assert np.array_equal(a, b)
+    for (a, sa), (b, sb) in zip(res[1][4], res[0][4]):
+        assert np.array_equal(a, b) and np.array_equal(sa, sb)
