@@ -118,6 +118,20 @@ RFX_API int rfx_selftest_rng(rfx_ctx * ctx, uint64_t out[2]);
  * sphere i (i < 16) or triangle i - 16 (16 <= i < 24), objects in insertion order within their kind; counts = {spheres, triangles}.
  * A test evaluates Sphere::trace's / Triangle::trace's accept expressions on every pixel against them. */
 RFX_API int rfx_selftest_primary_bounds(rfx_ctx * ctx, int32_t out[96], int32_t counts[2]);
+/* The same bounds as a pure host function (no device, no context), for tests that run without a GPU: cam = eye[3], view[9] (row-major),
+ * fov; spheres = n_spheres x (cx, cy, cz, r^2); tris = n_tris x (v0[3], axTrans[9] row-major: what Triangle::trace reads, Triangle.cpp:56-57). */
+RFX_API int rfx_selftest_primary_bounds_host(const float cam[13], uint32_t width, uint32_t height, int n_spheres, const float * spheres,
+                                             int n_tris, const float * tris, int32_t out[96]);
+/* diagnostic, pure host function: the candidate grid the library builds for the shadow queries of one far light (option "light_grids").
+ * light = origin[3], radius; spheres = n_spheres x (cx, cy, cz, r); box = lo[3], hi[3] of every point a shadow ray can start from;
+ * reach_diagonal = diagonal of the box of ALL ray origins (sizes the rounding-noise margin of the exact sphere test).  Returns
+ * uv = the two cell-coordinate rows (column = floor(uv[0..2] . p + uv[3]), row = floor(uv[4..6] . p + uv[7])), dims = {nx, ny}
+ * ({0, 0}: the light is too close for a grid), counts = {nx*ny + 1, items}; cell_start / items (sphere indices, cell after cell) are
+ * filled when their capacities suffice.  A test casts random jittered shadow rays and checks that every sphere the float32 test of
+ * Sphere.cpp:49-57 reports is listed in the cell of the ray's origin. */
+RFX_API int rfx_selftest_light_grid_host(const float light[4], int n_spheres, const float * spheres, const float box[6], float reach_diagonal,
+                                         float uv[8], int32_t dims[2], uint32_t * cell_start, uint64_t cell_cap, int32_t * items, uint64_t item_cap,
+                                         uint64_t counts[2]);
 
 /* ---- Render (reference Render.h:30-41) ----------------------------------------------------------------- */
 RFX_API int rfx_set_image_size(rfx_ctx * ctx, uint32_t width, uint32_t height);   /* Render::setImageSize, Render.cpp:57-80 */

@@ -53,6 +53,9 @@ SYMBOLS = [
     ("rfx_skip_samples", C.c_int, [C.c_void_p, C.c_uint64]),
     ("rfx_selftest_rng", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     ("rfx_selftest_primary_bounds", C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    ("rfx_selftest_primary_bounds_host", C.c_int, [_fp, C.c_uint32, C.c_uint32, C.c_int, _fp, C.c_int, _fp, C.POINTER(C.c_int32)]),
+    ("rfx_selftest_light_grid_host", C.c_int, [_fp, C.c_int, _fp, _fp, C.c_float, _fp, C.POINTER(C.c_int32), _u32p, C.c_uint64,
+                                              C.POINTER(C.c_int32), C.c_uint64, C.POINTER(C.c_uint64)]),
     ("rfx_set_image_size", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     ("rfx_render_begin", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("rfx_render_next", C.c_int, [C.c_void_p, C.c_uint32]),
@@ -113,6 +116,47 @@ class RfxError(RuntimeError):
 def _f(a):
     a = np.ascontiguousarray(a, dtype=np.float32)
     return a, a.ctypes.data_as(_fp)
+
+
+def primary_bounds_host(cam, width, height, spheres, tris):
+    """Pure host function (no GPU): the primary-ray screen bounds of ``spheres`` [(cx, cy, cz, r^2)] and ``tris`` [(v0[3], axTrans[9])]
+    for ``cam`` = (eye, view, fov): (sphere rectangles [nS][4], triangle rectangles [nT][4]) as x0, x1, y0, y1 inclusive."""
+    L = load()
+    eye, view, fov = cam
+    c = np.concatenate([np.asarray(eye, np.float32), np.asarray(view, np.float32), [np.float32(fov)]]).astype(np.float32)
+    sp = np.ascontiguousarray(np.asarray(spheres, np.float32).reshape(-1, 4)) if len(spheres) else np.zeros((0, 4), np.float32)
+    tr = np.ascontiguousarray(np.asarray([np.concatenate([np.asarray(t[0], np.float32), np.asarray(t[1], np.float32)]) for t in tris], np.float32).reshape(-1, 12)) \
+        if len(tris) else np.zeros((0, 12), np.float32)
+    out = (C.c_int32 * 96)()
+    rc = L.rfx_selftest_primary_bounds_host(c.ctypes.data_as(_fp), width, height, len(sp), sp.ctypes.data_as(_fp), len(tr), tr.ctypes.data_as(_fp), out)
+    if rc != 0:
+        raise RfxError("rfx_selftest_primary_bounds_host failed (%d)" % rc)
+    a = np.ctypeslib.as_array(out).reshape(24, 4).copy()
+    return a[:len(sp)], a[16:16 + len(tr)]
+
+
+def light_grid_host(light, spheres, box, reach_diagonal):
+    """Pure host function (no GPU): the shadow-ray candidate grid of one far light.  light = (ox, oy, oz, radius), spheres [n][4] =
+    (cx, cy, cz, r), box = (lo[3], hi[3]).  Returns None when the light is too close, else (uv[2][4], nx, ny, cell_start, items)."""
+    L = load()
+    lt = np.asarray(light, np.float32)
+    sp = np.ascontiguousarray(np.asarray(spheres, np.float32).reshape(-1, 4))
+    bx = np.asarray(box, np.float32).reshape(6)
+    uv = np.zeros(8, np.float32)
+    dims = (C.c_int32 * 2)()
+    counts = (C.c_uint64 * 2)()
+    args = (lt.ctypes.data_as(_fp), len(sp), sp.ctypes.data_as(_fp), bx.ctypes.data_as(_fp), C.c_float(reach_diagonal), uv.ctypes.data_as(_fp), dims)
+    rc = L.rfx_selftest_light_grid_host(*args, None, 0, None, 0, counts)
+    if rc != 0:
+        raise RfxError("rfx_selftest_light_grid_host failed (%d)" % rc)
+    if dims[0] == 0:
+        return None
+    cells = np.zeros(int(counts[0]), np.uint32)
+    items = np.zeros(max(int(counts[1]), 1), np.int32)
+    rc = L.rfx_selftest_light_grid_host(*args, cells.ctypes.data_as(_u32p), len(cells), items.ctypes.data_as(C.POINTER(C.c_int32)), len(items), counts)
+    if rc != 0:
+        raise RfxError("rfx_selftest_light_grid_host failed (%d)" % rc)
+    return uv.reshape(2, 4), int(dims[0]), int(dims[1]), cells, items[:int(counts[1])]
 
 
 def pack_cameras(cams):

@@ -1235,6 +1235,71 @@ int rfx_selftest_rng(rfx_ctx * ctx, uint64_t out[2])
   return RFX_OK;
 }
 
+// The two host-side bound computations as pure functions (no device, no context), so that the CPU test suite can check them against
+// the kernels' float32 expressions evaluated in numpy.
+int rfx_selftest_primary_bounds_host(const float cam[13], uint32_t width, uint32_t height, int n_spheres, const float * spheres,
+                                     int n_tris, const float * tris, int32_t out[96])
+{
+  if (!cam || !out || n_spheres < 0 || n_spheres > SMALL_MAX_SPHERES || n_tris < 0 || n_tris > SMALL_MAX_TRIS || (n_spheres && !spheres) || (n_tris && !tris) || !width || !height)
+    return RFX_ERR_ARG;
+  static SmallScene sc;          // (4 KB: off the stack)
+  memset(&sc, 0, sizeof(sc));
+  sc.nS = n_spheres; sc.nT = n_tris;
+  for (int i = 0; i < n_spheres; i++) sc.sph[i] = make_float4(spheres[4 * i], spheres[4 * i + 1], spheres[4 * i + 2], spheres[4 * i + 3]);
+  for (int k = 0; k < n_tris; k++)
+  {
+    memcpy(sc.tri[k].v0, tris + 12 * k, 12);
+    memcpy(sc.tri[k].ax, tris + 12 * k + 3, 36);
+  }
+  FrameParams fp;
+  memset(&fp, 0, sizeof(fp));
+  memcpy(fp.eye, cam, 12); memcpy(fp.view, cam + 3, 36);
+  fp.rz = float(width) / 2.0f / tanf(cam[12] / 2.0f);            // Render.cpp:148-150
+  fp.wHalf = width / 2.0f; fp.hHalf = height / 2.0f;
+  fp.W = width; fp.H = height;
+  const PrimaryCull pc = makePrimaryCull(sc, fp);
+  memcpy(out, pc.rect, sizeof(pc.rect));
+  return RFX_OK;
+}
+
+int rfx_selftest_light_grid_host(const float light[4], int n_spheres, const float * spheres, const float box[6], float reach_diagonal,
+                                 float uv[8], int32_t dims[2], uint32_t * cell_start, uint64_t cell_cap, int32_t * items, uint64_t item_cap,
+                                 uint64_t counts[2])
+{
+  if (!light || !spheres || !box || !uv || !dims || !counts || n_spheres <= 0) return RFX_ERR_ARG;
+  std::vector<HostObj> objs((size_t)n_spheres);
+  std::vector<const HostObj *> sph((size_t)n_spheres);
+  std::vector<BvhPrim> prims((size_t)n_spheres);
+  const double R = (double)reach_diagonal;
+  for (int i = 0; i < n_spheres; i++)
+  {
+    HostObj & o = objs[i];
+    memset(&o, 0, sizeof(o));
+    memcpy(o.center, spheres + 4 * i, 12);
+    o.radius = spheres[4 * i + 3];
+    o.sqRadius = o.radius * o.radius;                           // Sphere.cpp:13
+    sph[i] = &o;
+    BvhPrim & p = prims[i];
+    memcpy(p.c, o.center, 12); p.r = o.radius; p.index = i;
+    const double noise = std::min(3e-7 * R * R / std::max((double)p.r, 1e-30), 7.7e-4 * R);   // as uploadScene sizes the box margins
+    p.m = (float)(2.0 * noise + 1e-6 * R);
+  }
+  Light L;
+  memset(&L, 0, sizeof(L));
+  L.ox = light[0]; L.oy = light[1]; L.oz = light[2]; L.radius = light[3];
+  const double blo[3] = { box[0], box[1], box[2] }, bhi[3] = { box[3], box[4], box[5] };
+  LightGridHost lg;
+  counts[0] = counts[1] = 0;
+  dims[0] = dims[1] = 0;
+  if (!buildLightGrid(L, sph, prims, blo, bhi, lg)) return RFX_OK;      // no grid for this light: dims stay 0
+  memcpy(uv, lg.g.u, 16); memcpy(uv + 4, lg.g.v, 16);
+  dims[0] = lg.g.nx; dims[1] = lg.g.ny;
+  counts[0] = lg.cellStart.size(); counts[1] = lg.index.size();
+  if (cell_start && cell_cap >= lg.cellStart.size()) memcpy(cell_start, lg.cellStart.data(), lg.cellStart.size() * sizeof(uint32_t));
+  if (items && item_cap >= lg.index.size() && !lg.index.empty()) memcpy(items, lg.index.data(), lg.index.size() * sizeof(int32_t));
+  return RFX_OK;
+}
+
 int rfx_selftest_primary_bounds(rfx_ctx * ctx, int32_t out[96], int32_t counts[2])
 {
   if (!ctx || !out || !counts) return RFX_ERR_ARG;
