@@ -1,6 +1,6 @@
 // rfx_trace_blob.cu — K2 for scenes that do not fit the constant bank (config 4: 1024 spheres), every mode of Render::renderNext:
-//   k_trace_blob<MULTI>                    row-aligned slices, ARGB and/or float image; one sample per pixel or grid SSAA / additive jitter
-//   k_blob_wave_first + k_blob_wave_rest   one-sample ARGB frames of reflection depth >= 4 as a two-kernel wavefront (below)
+//   k_trace_blob<MULTI, GRIDS>             row-aligned slices, ARGB and/or float image; one sample per pixel or grid SSAA / additive jitter
+//   k_blob_wave_first<GRIDS> + k_blob_wave_rest   one-sample ARGB frames of reflection depth >= 3 as a two-kernel wavefront (below)
 //   k_trace_blob_any                       arbitrary pixel slices, block preview, signature runs
 //   k_trace_blob_rays                      Scene::trace for an explicit ray list (rfx_trace_rays)
 // All of them run ONE restatement of Scene::trace, traceBlob<SIG, MODE> (round 1 kept a second one, k_trace in rfx_kernels.cu, with two
@@ -18,8 +18,11 @@
 //   * Shadow queries towards a FAR light do not walk the hierarchy: their rays are nearly parallel, so the host bins the spheres'
 //     (inflated) shadows on a plane across the light's direction and the query tests the candidate list of its origin's cell with
 //     the exact arithmetic (LightGrid, rfx_capi.cu buildLightGrid) — an any-hit query only asks whether something is hit.
+//   * Neither does the FIRST query of a path: every path starts at the eye, so the host bins the spheres' primary-ray screen bounds
+//     into 32x32-pixel cells per camera (EyeGrid, buildEyeGrid) and the 32 lanes of a tile walk the same short list.
+//     (Both lists go through the same branch of intersectBlob; the queue-driven kernel is compiled without it: traceBlob.)
 //   * 4x8 pixel tiles per warp on a 2-D grid, 128-bit framebuffer stores, 64 registers / 8 CTAs per SM.
-// Each step was measured (profiles/README.md: 6.66 -> 3.80 ms for a 3840x2160 frame of the 1024-sphere scene at depth 8).
+// Each step was measured (profiles/README.md: 6.66 -> 3.63 ms for a 3840x2160 frame of the 1024-sphere scene at depth 8, 1.19 -> 0.57 at depth 1).
 //
 // ARITHMETIC CONTRACT: as in rfx_trace_small.cu — --fmad=false, every + - * / sqrtf of the reference's arithmetic is the IEEE
 // binary32 RN operation in the reference's evaluation order; the expressions below are the ones of rfx_trace_small.cu.
