@@ -678,6 +678,15 @@ int uploadScene(rfx_ctx * ctx, cudaStream_t st)
       ss.sph[i] = make_float4(sph[i]->center[0], sph[i]->center[1], sph[i]->center[2], sph[i]->sqRadius);
       ss.mat[i] = sph[i]->mat;
     }
+    // the sphere loop of the kernels runs over whole quads: pad with NaN records (their discriminant is NaN: never a hit)
+    static_assert(SMALL_MAX_SPHERES % 4 == 0, "quads");
+    for (size_t i = sph.size(); i % 4 != 0; i++)
+    {
+      const float qnan = std::numeric_limits<float>::quiet_NaN();
+      ss.sph[i] = make_float4(qnan, qnan, qnan, qnan);
+      ss.mat[i].order = 0x7FFFFFFF;
+      ss.nS = (int)i + 1;
+    }
     for (size_t i = 0; i < tri.size(); i++)
     {
       const Triangle & t = tri[i]->tri;
@@ -1320,7 +1329,8 @@ int rfx_selftest_primary_bounds(rfx_ctx * ctx, int32_t out[96], int32_t counts[2
   const PrimaryCull pc = makePrimaryCull(ctx->small, fp);
   static_assert(sizeof(pc.rect) == 96 * sizeof(int32_t), "24 rectangles of 4 ints");
   memcpy(out, pc.rect, sizeof(pc.rect));
-  counts[0] = ctx->small.nS; counts[1] = ctx->small.nT;
+  counts[0] = 0; counts[1] = ctx->small.nT;
+  for (const HostObj & o : ctx->objs) counts[0] += o.kind == 0;      // (small.nS is padded to whole quads)
   return RFX_OK;
 }
 

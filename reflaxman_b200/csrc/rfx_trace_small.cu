@@ -36,9 +36,6 @@ namespace rfx
 #define RFX_TILE_W 4u      // pixel tile of one warp: RFX_TILE_W x RFX_TILE_H = 32 (4x8 measured best, profiles/variants_d_r1.jsonl)
 #endif
 #define RFX_TILE_H (32u / RFX_TILE_W)
-#ifndef RFX_SPHERE_GROUP
-#define RFX_SPHERE_GROUP 4     // spheres per loop trip: 1, 2 or 4 (profiles/README.md)
-#endif
 #ifndef RFX_TILE_BOUNDS
 // cost classes of the tile scheduler: class c holds the tile groups whose longest path has >= bound[c] segments (last class: the rest)
 #define RFX_TILE_BOUNDS { 8u, 4u, 2u }
@@ -57,9 +54,6 @@ namespace rfx
 #endif
 #ifndef RFX_PRIMARY_CULL
 #define RFX_PRIMARY_CULL 1         // the first query of a path (origin = eye) skips the object-loop trips whose screen bounds miss the warp's tile
-#endif
-#if RFX_PRIMARY_CULL && RFX_SPHERE_GROUP != 4
-#error "RFX_PRIMARY_CULL ranges are in sphere quads: RFX_SPHERE_GROUP must be 4"
 #endif
 #ifndef RFX_SMALL_MINBLOCKS
 #define RFX_SMALL_MINBLOCKS 8      // fast kernel: 64 registers, no spills, 32 warps per SM
@@ -136,18 +130,19 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
         }                                                                                    \
       }                                                                                      \
     }
-  const int endOff = sc.nS << 4;
-  int off = RANGED ? range.s0 : 0;
-  // Several spheres per trip: their reject chains are independent (ILP for a scheduler that holds ~7 warps), they share the
+  // Four spheres per trip: their reject chains are independent (ILP for a scheduler that holds ~7 warps), they share the
   // loop bookkeeping, and ONE divergent region gates all their tails (the common case — no lane passes any gate — costs one
   // branch).  The discriminants of a trip are evaluated before its tails, so an any-hit lane that closes in an earlier tail
-  // (a4 becomes NaN) must not enter a later one.
-#if RFX_SPHERE_GROUP == 4
-  const int endQuad = RANGED ? range.s1 : (endOff & ~63);
+  // (a4 becomes NaN) must not enter a later one.  The host pads the sphere array to whole quads with NaN records, whose
+  // discriminant is NaN and whose gate stays shut: no remainder loops — 350 SASS instructions (three more copies of the tail) that
+  // the demo scene never executed and that still cost 3 % of the kernel (202.0 -> 195.9 us: the instruction cache is that tight).
+  // (ONE copy of the tail, walked per lane over its open gates, is 184 instructions less again but 2 % slower: profiles/r2_prim.)
+  const int endQuad = RANGED ? range.s1 : (sc.nS << 4);
+  int off = RANGED ? range.s0 : 0;
 #pragma unroll 1
   for (; off != endQuad; off += 64)
   {
-    asm volatile("" : "+r"(off));
+    asm volatile("" : "+r"(off));   // keeps `off` the only induction variable (ptxas otherwise strength-reduces it into five)
     RFX_SPHERE_REJECT(off, s0, b0, disc0)
     RFX_SPHERE_REJECT(off + 16, s1, b1, disc1)
     RFX_SPHERE_REJECT(off + 32, s2, b2, disc2)
@@ -160,31 +155,6 @@ __device__ __forceinline__ void intersectSmall(const SmallScene & sc, V3 o, V3 d
       if (g2 && a4 == a4) RFX_SPHERE_TAIL(off + 32, b2, disc2)
       if (g3 && a4 == a4) RFX_SPHERE_TAIL(off + 48, b3, disc3)
     }
-  }
-  if (RANGED) off = endOff & ~63;          // the spheres past the last whole quad are tested on every query
-#endif
-#if RFX_SPHERE_GROUP >= 2
-  const int endPair = endOff & ~31;
-#pragma unroll 1
-  for (; off != endPair; off += 32)
-  {
-    asm volatile("" : "+r"(off));
-    RFX_SPHERE_REJECT(off, s0, b0, disc0)
-    RFX_SPHERE_REJECT(off + 16, s1, b1, disc1)
-    const bool g0 = RFX_SPHERE_GATE(b0, disc0), g1 = RFX_SPHERE_GATE(b1, disc1);
-    if (g0 || g1)
-    {
-      if (g0) RFX_SPHERE_TAIL(off, b0, disc0)
-      if (g1 && a4 == a4) RFX_SPHERE_TAIL(off + 16, b1, disc1)
-    }
-  }
-#endif
-#pragma unroll 1
-  for (; off != endOff; off += 16)
-  {
-    asm volatile("" : "+r"(off));   // keeps `off` the only induction variable (ptxas otherwise strength-reduces it into five)
-    RFX_SPHERE_REJECT(off, s0, b0, disc0)
-    if (RFX_SPHERE_GATE(b0, disc0)) RFX_SPHERE_TAIL(off, b0, disc0)
   }
 #undef RFX_SPHERE_GATE
 #undef RFX_SPHERE_REJECT
@@ -299,7 +269,7 @@ __device__ __forceinline__ V3 traceSmall(const SmallScene & sc, V3 origin, V3 ra
     Best hit;
     hit.dist = FLT_MAX; hit.slot = -1; hit.order = 0x7FFFFFFF; hit.t = 0; hit.u = 0; hit.v = 0;
     intersectSmall<FEAT, RANGED>(sc, qo, qd, shadowQuery ? hslot : -1, shadowQuery, hit, range);
-    if (RANGED) { range.s0 = 0; range.s1 = (sc.nS << 4) & ~63; range.t0 = 0; range.t1 = sc.nT * 48; }   // rematerialised from the constant bank
+    if (RANGED) { range.s0 = 0; range.s1 = sc.nS << 4; range.t0 = 0; range.t1 = sc.nT * 48; }   // rematerialised from the constant bank
 
     V3 sumLight = (FEAT & F_LIGHTS) ? carryLight : mk(0.0f, 0.0f, 0.0f);
     V3 sumSpec = (FEAT & F_LIGHTS) ? carrySpec : mk(0.0f, 0.0f, 0.0f);
@@ -599,7 +569,7 @@ PrimaryCull makePrimaryCull(const SmallScene & sc, const FrameParams & fp)
   for (int i = 0; i < SMALL_MAX_SPHERES + SMALL_MAX_TRIS; i++) pc.rect[i] = cullFull();
   const PrimaryCamera cam = makePrimaryCamera(fp);
   if (!cam.ok) return pc;
-  for (int i = 0; i < sc.nS && i < SMALL_MAX_SPHERES; i++) pc.rect[i] = primarySphereBounds(cam, sc.sph[i]);
+  for (int i = 0; i < sc.nS && i < SMALL_MAX_SPHERES; i++) pc.rect[i] = sc.sph[i].x == sc.sph[i].x ? primarySphereBounds(cam, sc.sph[i]) : cullNone();   // NaN: padding
   for (int k = 0; k < sc.nT && k < SMALL_MAX_TRIS; k++)
     pc.rect[SMALL_MAX_SPHERES + k] = cullTriangle(cam.c[0], cam.c[1], cam.c[2], cam.eye, cam.rz, cam.wHalf, cam.hHalf, cam.W, cam.H, sc.tri[k]);
   return pc;
@@ -700,7 +670,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, MULTI ? 7 : RFX_SMALL_MINBLOCKS
     const int4 r = pc.rect[lane < SMALL_MAX_SPHERES + SMALL_MAX_TRIS ? lane : 0];
     const bool seen = lane < SMALL_MAX_SPHERES + SMALL_MAX_TRIS && tx0 + (int)RFX_TILE_W - 1 >= r.x && tx0 <= r.y && ty0 + (int)RFX_TILE_H - 1 >= r.z && ty0 <= r.w;
     const uint32_t m = __ballot_sync(0xffffffffu, seen);
-    const uint32_t ms = m & ((1u << (sc.nS & ~3)) - 1u);                 // spheres of whole quads (the rest is always tested)
+    const uint32_t ms = m & ((1u << sc.nS) - 1u);
     const uint32_t mq = (ms | (ms >> 1) | (ms >> 2) | (ms >> 3)) & 0x1111u;   // bit 4q: quad q has a candidate
     if (mq) { first.s0 = (__ffs(mq) - 1) << 4; first.s1 = ((31 - __clz(mq)) << 4) + 64; }
     const uint32_t mt = (m >> SMALL_MAX_SPHERES) & ((1u << sc.nT) - 1u);

@@ -90,7 +90,7 @@ constexpr int SMALL_MAX_OBJECTS = SMALL_MAX_SPHERES + SMALL_MAX_TRIS + SMALL_MAX
 
 struct SmallScene
 {
-  int nS, nT, nP, nL;
+  int nS, nT, nP, nL;                       // nS: spheres padded to whole quads with NaN records (never hit)
   int skyTex;
   float halfTileW, halfTileH;
   float ambientPower;
