@@ -1251,7 +1251,8 @@ int rfx_selftest_primary_bounds_host(const float cam[13], uint32_t width, uint32
 {
   if (!cam || !out || n_spheres < 0 || n_spheres > SMALL_MAX_SPHERES || n_tris < 0 || n_tris > SMALL_MAX_TRIS || (n_spheres && !spheres) || (n_tris && !tris) || !width || !height)
     return RFX_ERR_ARG;
-  static SmallScene sc;          // (4 KB: off the stack)
+  std::vector<SmallScene> holder(1);   // (4 KB: off the stack)
+  SmallScene & sc = holder[0];
   memset(&sc, 0, sizeof(sc));
   sc.nS = n_spheres; sc.nT = n_tris;
   for (int i = 0; i < n_spheres; i++) sc.sph[i] = make_float4(spheres[4 * i], spheres[4 * i + 1], spheres[4 * i + 2], spheres[4 * i + 3]);
