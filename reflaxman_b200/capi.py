@@ -56,6 +56,8 @@ SYMBOLS = [
     ("rfx_selftest_primary_bounds_host", C.c_int, [_fp, C.c_uint32, C.c_uint32, C.c_int, _fp, C.c_int, _fp, C.POINTER(C.c_int32)]),
     ("rfx_selftest_light_grid_host", C.c_int, [_fp, C.c_int, _fp, _fp, C.c_float, _fp, C.POINTER(C.c_int32), _u32p, C.c_uint64,
                                               C.POINTER(C.c_int32), C.c_uint64, C.POINTER(C.c_uint64)]),
+    ("rfx_selftest_eye_grid_host", C.c_int, [_fp, C.c_uint32, C.c_uint32, C.c_int, _fp, C.POINTER(C.c_int32), _u32p, C.c_uint64,
+                                            C.POINTER(C.c_int32), C.c_uint64, C.POINTER(C.c_uint64)]),
     ("rfx_set_image_size", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     ("rfx_render_begin", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("rfx_render_next", C.c_int, [C.c_void_p, C.c_uint32]),
@@ -157,6 +159,27 @@ def light_grid_host(light, spheres, box, reach_diagonal):
     if rc != 0:
         raise RfxError("rfx_selftest_light_grid_host failed (%d)" % rc)
     return uv.reshape(2, 4), int(dims[0]), int(dims[1]), cells, items[:int(counts[1])]
+
+
+def eye_grid_host(cam, width, height, spheres):
+    """Pure host function (no GPU): the screen grid of the first query for ``cam`` and spheres [n][4] = (cx, cy, cz, r^2).
+    Returns None when the camera gets no grid, else (nx, ny, shift, cell_start, items)."""
+    L = load()
+    eye, view, fov = cam
+    c = np.concatenate([np.asarray(eye, np.float32), np.asarray(view, np.float32), [np.float32(fov)]]).astype(np.float32)
+    sp = np.ascontiguousarray(np.asarray(spheres, np.float32).reshape(-1, 4))
+    dims = (C.c_int32 * 3)()
+    counts = (C.c_uint64 * 2)()
+    args = (c.ctypes.data_as(_fp), width, height, len(sp), sp.ctypes.data_as(_fp), dims)
+    if L.rfx_selftest_eye_grid_host(*args, None, 0, None, 0, counts) != 0:
+        raise RfxError("rfx_selftest_eye_grid_host failed")
+    if dims[0] == 0:
+        return None
+    cells = np.zeros(int(counts[0]), np.uint32)
+    items = np.zeros(max(int(counts[1]), 1), np.int32)
+    if L.rfx_selftest_eye_grid_host(*args, cells.ctypes.data_as(_u32p), len(cells), items.ctypes.data_as(C.POINTER(C.c_int32)), len(items), counts) != 0:
+        raise RfxError("rfx_selftest_eye_grid_host failed")
+    return int(dims[0]), int(dims[1]), int(dims[2]), cells, items[:int(counts[1])]
 
 
 def pack_cameras(cams):

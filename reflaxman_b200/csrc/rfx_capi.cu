@@ -750,6 +750,53 @@ int rankSamples(rfx_ctx * ctx, uint64_t n, bool skipOnly, cudaStream_t st, uint6
 // the exact test, SSAA sub-samples and jitter) cover its pixel.  The host bins the rectangles into 32x32-pixel cells per camera; a
 // 4x8 tile lies in one cell, so its 32 lanes walk the same short list instead of the hierarchy.  Closest hit over a complete
 // candidate list is the hierarchy walk's answer (ties go to the lower insertion index in both).
+constexpr int EYE_GRID_SHIFT = 5;      // 32x32-pixel cells: a 4x8 tile of the kernels lies in one cell
+
+// the binning itself, a pure function (rfx_selftest_eye_grid_host checks it on the CPU): spheres[i] = (cx, cy, cz, r^2)
+bool binEyeGrid(const FrameParams & fp, const std::vector<float4> & spheres, int & nx, int & ny, std::vector<uint32_t> & cells,
+                std::vector<float4> & items, std::vector<int> & index)
+{
+  const PrimaryCamera cam = makePrimaryCamera(fp);
+  if (!cam.ok || fp.W == 0 || fp.H == 0) return false;
+  const int shift = EYE_GRID_SHIFT;
+  nx = (int)((fp.W + 31u) >> shift); ny = (int)((fp.H + 31u) >> shift);
+  if ((uint64_t)nx * ny > (1u << 22)) return false;
+  struct Span { int x0, x1, y0, y1; };
+  std::vector<Span> spans(spheres.size());
+  cells.assign((size_t)nx * ny + 1, 0);
+  for (size_t i = 0; i < spheres.size(); i++)
+  {
+    const int4 r = primarySphereBounds(cam, spheres[i]);
+    Span sp = { 1, 0, 1, 0 };
+    if (r.x <= r.y && r.z <= r.w && r.y >= 0 && r.w >= 0 && r.x < (int)fp.W && r.z < (int)fp.H)
+    {
+      sp.x0 = std::max(r.x, 0) >> shift; sp.x1 = std::min(r.y, (int)fp.W - 1) >> shift;
+      sp.y0 = std::max(r.z, 0) >> shift; sp.y1 = std::min(r.w, (int)fp.H - 1) >> shift;
+      for (int y = sp.y0; y <= sp.y1; y++)
+        for (int x = sp.x0; x <= sp.x1; x++) cells[(size_t)y * nx + x]++;
+    }
+    spans[i] = sp;
+  }
+  uint32_t run = 0;
+  for (size_t c = 0; c < (size_t)nx * ny; c++) { const uint32_t k = cells[c]; cells[c] = run; run += k; }
+  cells[(size_t)nx * ny] = run;
+  items.assign(std::max<uint32_t>(run, 1), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+  index.assign(std::max<uint32_t>(run, 1), 0);
+  std::vector<uint32_t> fill(cells.begin(), cells.end() - 1);
+  for (size_t i = 0; i < spheres.size(); i++)
+  {
+    const Span & sp = spans[i];
+    for (int y = sp.y0; y <= sp.y1; y++)
+      for (int x = sp.x0; x <= sp.x1; x++)
+      {
+        const uint32_t k = fill[(size_t)y * nx + x]++;
+        items[k] = spheres[i];
+        index[k] = (int)i;
+      }
+  }
+  return true;
+}
+
 int buildEyeGrid(rfx_ctx * ctx, const FrameParams & fp, cudaStream_t st)
 {
   ctx->eyeGrid.cellStart = nullptr;
@@ -764,47 +811,13 @@ int buildEyeGrid(rfx_ctx * ctx, const FrameParams & fp, cudaStream_t st)
     return RFX_OK;
   }
   ctx->eyeValid = false;
-  const PrimaryCamera cam = makePrimaryCamera(fp);
-  if (!cam.ok || fp.W == 0 || fp.H == 0) return RFX_OK;
-  const int shift = 5;
-  const int nx = (int)((fp.W + 31u) >> shift), ny = (int)((fp.H + 31u) >> shift);
-  if ((uint64_t)nx * ny > (1u << 22)) return RFX_OK;
-  struct Span { int x0, x1, y0, y1; };
-  std::vector<Span> spans;
-  std::vector<const HostObj *> sph;
-  for (const HostObj & o : ctx->objs) if (o.kind == 0) sph.push_back(&o);
-  spans.resize(sph.size());
-  std::vector<uint32_t> cells((size_t)nx * ny + 1, 0);
-  for (size_t i = 0; i < sph.size(); i++)
-  {
-    const int4 r = primarySphereBounds(cam, make_float4(sph[i]->center[0], sph[i]->center[1], sph[i]->center[2], sph[i]->sqRadius));
-    Span sp = { 1, 0, 1, 0 };
-    if (r.x <= r.y && r.z <= r.w && r.y >= 0 && r.w >= 0 && r.x < (int)fp.W && r.z < (int)fp.H)
-    {
-      sp.x0 = std::max(r.x, 0) >> shift; sp.x1 = std::min(r.y, (int)fp.W - 1) >> shift;
-      sp.y0 = std::max(r.z, 0) >> shift; sp.y1 = std::min(r.w, (int)fp.H - 1) >> shift;
-      for (int y = sp.y0; y <= sp.y1; y++)
-        for (int x = sp.x0; x <= sp.x1; x++) cells[(size_t)y * nx + x]++;
-    }
-    spans[i] = sp;
-  }
-  uint32_t run = 0;
-  for (size_t c = 0; c < (size_t)nx * ny; c++) { const uint32_t k = cells[c]; cells[c] = run; run += k; }
-  cells[(size_t)nx * ny] = run;
-  std::vector<float4> items(std::max<uint32_t>(run, 1));
-  std::vector<int> index(std::max<uint32_t>(run, 1));
-  std::vector<uint32_t> fill(cells.begin(), cells.end() - 1);
-  for (size_t i = 0; i < sph.size(); i++)
-  {
-    const Span & sp = spans[i];
-    for (int y = sp.y0; y <= sp.y1; y++)
-      for (int x = sp.x0; x <= sp.x1; x++)
-      {
-        const uint32_t k = fill[(size_t)y * nx + x]++;
-        items[k] = make_float4(sph[i]->center[0], sph[i]->center[1], sph[i]->center[2], sph[i]->sqRadius);
-        index[k] = (int)i;
-      }
-  }
+  std::vector<float4> spheres;       // in the order of the sorted sphere array (uploadScene walks the objects the same way)
+  for (const HostObj & o : ctx->objs) if (o.kind == 0) spheres.push_back(make_float4(o.center[0], o.center[1], o.center[2], o.sqRadius));
+  int nx = 0, ny = 0;
+  std::vector<uint32_t> cells;
+  std::vector<float4> items;
+  std::vector<int> index;
+  if (!binEyeGrid(fp, spheres, nx, ny, cells, items, index)) return RFX_OK;
   int rc;
   if ((rc = ensure(ctx, ctx->dEyeCells, ctx->eyeCellsCap, cells.size())) != RFX_OK) return rc;
   if ((rc = ensure(ctx, ctx->dEyeSpheres, ctx->eyeSpheresCap, items.size())) != RFX_OK) return rc;
@@ -816,7 +829,7 @@ int buildEyeGrid(rfx_ctx * ctx, const FrameParams & fp, cudaStream_t st)
   CK(cudaMemcpyAsync(ctx->dEyeIndex, index.data(), index.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   ctx->stats.h2d_bytes += cells.size() * 4 + items.size() * 16 + index.size() * 4;
   ctx->eyeGrid.cellStart = ctx->dEyeCells; ctx->eyeGrid.itemSphere = ctx->dEyeSpheres; ctx->eyeGrid.itemIndex = ctx->dEyeIndex;
-  ctx->eyeGrid.nx = nx; ctx->eyeGrid.ny = ny; ctx->eyeGrid.shift = shift;
+  ctx->eyeGrid.nx = nx; ctx->eyeGrid.ny = ny; ctx->eyeGrid.shift = EYE_GRID_SHIFT;
   memcpy(ctx->eyeKey, key, sizeof(key)); ctx->eyeSceneKey = ctx->sceneUploads; ctx->eyeValid = true;
   ctx->eyeGridBuilds++;
   return RFX_OK;
@@ -1307,6 +1320,31 @@ int rfx_selftest_light_grid_host(const float light[4], int n_spheres, const floa
   counts[0] = lg.cellStart.size(); counts[1] = lg.index.size();
   if (cell_start && cell_cap >= lg.cellStart.size()) memcpy(cell_start, lg.cellStart.data(), lg.cellStart.size() * sizeof(uint32_t));
   if (items && item_cap >= lg.index.size() && !lg.index.empty()) memcpy(items, lg.index.data(), lg.index.size() * sizeof(int32_t));
+  return RFX_OK;
+}
+
+int rfx_selftest_eye_grid_host(const float cam[13], uint32_t width, uint32_t height, int n_spheres, const float * spheres, int32_t dims[3],
+                               uint32_t * cell_start, uint64_t cell_cap, int32_t * items, uint64_t item_cap, uint64_t counts[2])
+{
+  if (!cam || !spheres || !dims || !counts || n_spheres <= 0 || !width || !height) return RFX_ERR_ARG;
+  FrameParams fp;
+  memset(&fp, 0, sizeof(fp));
+  memcpy(fp.eye, cam, 12); memcpy(fp.view, cam + 3, 36);
+  fp.rz = float(width) / 2.0f / tanf(cam[12] / 2.0f);            // Render.cpp:148-150
+  fp.wHalf = width / 2.0f; fp.hHalf = height / 2.0f;
+  fp.W = width; fp.H = height;
+  std::vector<float4> sp((size_t)n_spheres);
+  for (int i = 0; i < n_spheres; i++) sp[i] = make_float4(spheres[4 * i], spheres[4 * i + 1], spheres[4 * i + 2], spheres[4 * i + 3]);
+  int nx = 0, ny = 0;
+  std::vector<uint32_t> cells;
+  std::vector<float4> rec;
+  std::vector<int> index;
+  dims[0] = dims[1] = dims[2] = 0; counts[0] = counts[1] = 0;
+  if (!binEyeGrid(fp, sp, nx, ny, cells, rec, index)) return RFX_OK;      // no grid for this camera: dims stay 0
+  dims[0] = nx; dims[1] = ny; dims[2] = EYE_GRID_SHIFT;
+  counts[0] = cells.size(); counts[1] = cells.back();
+  if (cell_start && cell_cap >= cells.size()) memcpy(cell_start, cells.data(), cells.size() * sizeof(uint32_t));
+  if (items && item_cap >= cells.back() && cells.back()) memcpy(items, index.data(), (size_t)cells.back() * sizeof(int32_t));
   return RFX_OK;
 }
 

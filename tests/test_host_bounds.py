@@ -140,3 +140,41 @@ def test_light_grid_host_lists_every_sphere_a_shadow_ray_can_hit(capi, seed):
 def test_light_grid_host_declines_a_near_light(capi):
     spheres = np.array([[0, 1, 0, 1], [3, 0.5, 1, 0.5]], F)
     assert capi.light_grid_host((2.0, 6.0, -1.0, 0.5), spheres, (-5, 0, -5, 5, 3, 5), 30.0) is None
+
+
+@pytest.mark.parametrize("which", ["grid16", "cloud"])
+def test_eye_grid_host_lists_every_sphere_a_primary_ray_can_hit(capi, which):
+    """The screen grid of a path's first query (blob scenes): for 113 cameras per scene — orbit, inside spheres, under the floor, looking
+    away — every sphere whose float32 accept expression (Sphere.cpp:49-57) a pixel's primary ray passes, or the ray through the far
+    corner of the pixel's SSAA / jitter footprint, is listed in the pixel's 32x32 cell; and the lists are short."""
+    if which == "grid16":
+        scene = S.synthetic_scene(16)
+    else:
+        rng = np.random.default_rng(78)
+        objs = []
+        for i in range(180):
+            r = float(10 ** rng.uniform(-1.5, 0.3))
+            c = rng.uniform([-8, 0, -6], [8, 5, 6])
+            objs.append(("sphere", (float(c[0]), float(c[1]) + r, float(c[2])), r, i % 2, (1.0, 1.0, 1.0), 0.5, 0.0))
+        scene = {"objects": objs}
+    sph, _ = P.scene_arrays(scene)
+    n = len(sph)
+    W, H = 200, 120
+    listed = cells_total = 0
+    for eye, view, fov in P.random_cameras(100, 9, sph):
+        g = capi.eye_grid_host((eye, view, fov), W, H, sph)
+        assert g is not None
+        nx, ny, shift, cells, items = g
+        assert (nx, ny, shift) == ((W + 31) // 32, (H + 31) // 32, 5)
+        member = np.zeros((nx * ny, n), bool)
+        for cell in range(nx * ny):
+            member[cell, items[cells[cell]:cells[cell + 1]]] = True
+        cell_of = ((np.arange(H)[:, None] >> shift) * nx + (np.arange(W)[None, :] >> shift))
+        rz = F(F(W) / F(2) / F(math.tan(F(fov) / F(2))))
+        for offx, offy in ((0.0, 0.0), (1.99, 1.99)):
+            d = P.primary_rays(eye, view, rz, F(W) / F(2), F(H) / F(2), W, H, offx, offy)
+            for i, s in enumerate(sph):
+                acc = P.sphere_accept(eye, d, s)
+                assert not (acc & ~member[cell_of, i]).any(), (which, i)
+        listed += len(items); cells_total += nx * ny
+    assert listed < 0.35 * n * cells_total, (listed, cells_total)
